@@ -1,0 +1,93 @@
+/* plm_chem.h -- C ABI of libplmchem.so: the B200 (sm_100a) drop-in for PelePhysics' per-cell
+ * chemistry operator.  Plain C types only; every entry point cites the reference interface it replaces.
+ *
+ * Pointers handed to the react/eval calls may be DEVICE pointers (GPU-built AMReX: all Array4 data is
+ * device accessible, PeleLM.cpp:5752-5758) or HOST pointers (CPU-built caller): the library asks the
+ * CUDA runtime which it is and stages host data through its own device buffers.  There is no CPU
+ * compute path: every call fails with PLM_ERR_NO_DEVICE when no sm_100-class GPU is present.
+ */
+#ifndef PLM_CHEM_H
+#define PLM_CHEM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* amrex::Array4<T> as a POD (amrex/Src/Base/AMReX_Array4.H:15-23):
+ * element (i,j,k,n) = p[(i-lo[0]) + (j-lo[1])*jstride + (k-lo[2])*kstride + n*nstride] */
+typedef struct { double* p; int64_t jstride, kstride, nstride; int lo[3], hi[3]; int ncomp; } plm_a4d;
+typedef struct { int*    p; int64_t jstride, kstride, nstride; int lo[3], hi[3]; int ncomp; } plm_a4i;
+
+typedef struct plm_reactor plm_reactor; /* opaque: one (mechanism, integrator) pair; ReactorBase object */
+
+enum { PLM_OK = 0, PLM_ERR_ARG = -1, PLM_ERR_NO_DEVICE = -2, PLM_ERR_CUDA = -3, PLM_ERR_MECH = -4,
+       PLM_ERR_INTEGRATION = -5 };
+
+/* per-cell status written by the integrators (replaces cvodeErrHandler -> amrex::Abort,
+ * ReactorCvodeUtils.cpp:9-21): 0 ok, else the CVODE flag of the failure (-1 too much work,
+ * -2 too much accuracy, -3 error-test failures, -4 convergence failures, -22 bad ewt, -27 tout too close) */
+
+/* counters summed over the cells of the last react call (ReactorCvode::print_final_stats,
+ * ReactorCvode.cpp:1929-1992) plus what the roofline needs */
+typedef struct {
+  int64_t ncells, nskipped;      /* integrated / masked (mask == -1) */
+  int64_t nst, nfe, nje, nsetups, nni, ncfn, netf;
+  int64_t nfailed;               /* cells with status != 0 */
+  int64_t max_fc, min_fc;
+  double  kernel_ms;             /* device time of the integration kernel (CUDA events) */
+} plm_stats;
+
+/* ReactorBase::create(name) (Factory.H:73-80; PeleLM.cpp:701-709).
+ * mechanism: "LiDryer" | "drm19" | "dodecane_lu"; integrator: "ReactorCvode" | "ReactorRK64". */
+int  plm_reactor_create(plm_reactor** out, const char* mechanism, const char* integrator);
+
+/* ReactorBase::init(reactor_type, ncells) + the ParmParse keys it reads
+ * (ReactorCvode.cpp:9-31 ode.{rtol,atol,max_nls_iters,clean_init_massfrac}, :722-726 cvode.{solve_type,max_order};
+ * ReactorRK64.cpp:14-20 ode.rk64_nsubsteps_{guess,min,max}).  reactor_type: 2 = h (HP; PeleLM). 1 (e) is not built.
+ * solve_type: "denseAJ_direct" (analytic Jacobian) | "dense_direct" (difference-quotient Jacobian). */
+int  plm_reactor_init(plm_reactor*, int reactor_type, double rtol, double atol, int max_order, int max_nls_iters,
+                      int clean_init_massfrac, const char* solve_type, int rk64_guess, int rk64_min, int rk64_max);
+
+/* ReactorBase::set_typ_vals_ode (ReactorBase.cpp:29-56): N+1 values; typ[0] > 0 => atol_k = typ_k * atol */
+int  plm_reactor_set_typ_vals(plm_reactor*, const double* typ, int n);
+
+/* ReactorBase::react(box, rY, rYsrc, T, rEner, rEner_src, FC, mask, dt_react, time [,stream])
+ * (ReactorBase.H:26-41; CPU semantics of ReactorCvode.cpp:1372-1453 / ReactorRK64.cpp:167-327).
+ * dt_react/time are not modified (PeleLM is not built with MOD_REACTOR).  Returns <0 on failure,
+ * else 0; per-cell failures are reported through plm_reactor_stats().nfailed and the status array. */
+int  plm_react_box(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rY, plm_a4d rYsrc, plm_a4d T,
+                   plm_a4d rEner, plm_a4d rEner_src, plm_a4d FC, plm_a4i mask,
+                   double* dt_react, double* time, void* cuda_stream);
+
+/* ReactorBase::react(rY_in, rYsrc_in, rX_in, rX_src_in, dt_react, time, ncells [,stream])
+ * (ReactorBase.H:43-55): AoS rY [ncells][N+1] incl. T, rYsrc [ncells][N], rX / rX_src [ncells]. */
+int  plm_react_flat(plm_reactor*, double* rY, double* rYsrc, double* rX, double* rX_src,
+                    double* dt_react, double* time, int ncells, void* cuda_stream);
+
+int  plm_reactor_stats(plm_reactor*, plm_stats* out);
+/* status word per cell of the last call, in box order (device or host destination) */
+int  plm_reactor_cell_status(plm_reactor*, int* dst, int64_t ncells);
+/* ReactorBase::close() (ReactorCvode.cpp:1908-1927; PeleLM.cpp:930) */
+void plm_reactor_close(plm_reactor*);
+
+int  plm_num_species(const plm_reactor*);
+const char* plm_last_error(void);
+
+/* ---- kernel-level entry points used by the parity tests (reference functions they mirror) ---- */
+/* utils::fKernelSpec (ReactorUtils.H:274-332): y [ncells][N+1], ydot [ncells][N+1] */
+int  plm_eval_rhs(plm_reactor*, int ncells, double t, const double* y, const double* rhoe_init,
+                  const double* rhoesrc_ext, const double* rYsrc, double* ydot, void* cuda_stream);
+/* cvode::cJac (ReactorCvodeJacobian.cpp:84-153): J [ncells][(N+1)^2] column-major */
+int  plm_eval_jac(plm_reactor*, int ncells, const double* y, double* J, void* cuda_stream);
+
+/* ---- cost model / load balance (PeleLM::getFuncCountDM PeleLM.cpp:5529-5623;
+ *      DistributionMapping::KnapSackProcessorMap AMReX_DistributionMapping.cpp:576-870) ---- */
+/* per-box cost = sum over the box of FC (device reduction); boxes given as consecutive cell ranges */
+int  plm_box_costs(const double* FC, const int64_t* box_offsets, int nboxes, int64_t* costs, void* cuda_stream);
+int  plm_knapsack(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack,
+                  int nmax, int* rank_of_box, double* efficiency);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,61 @@
+"""Build libplmchem.so (sm_100a only) in-tree with nvcc. Used by __graft_entry__.build() and the tests."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libplmchem.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+SOURCES = ["kernels.cu", "capi.cpp", "dev_tables.cpp", "knapsack.cpp", "gen/tables_LiDryer.c", "gen/tables_drm19.c",
+           "gen/tables_dodecane_lu.c"]
+
+
+def _newer(src: str, dst: str) -> bool:
+    return (not os.path.exists(dst)) or os.path.getmtime(src) > os.path.getmtime(dst)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers += [os.path.join(CSRC, "gen", "mech_tables.h"), os.path.join(os.path.dirname(HERE), "include", "plm_chem.h")]
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    objs = []
+    relink = force or not os.path.exists(LIB)
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(objdir, os.path.basename(s) + ".o")
+        objs.append(obj)
+        if force or _newer(src, obj) or os.path.getmtime(obj) < hdr_time:
+            if s.endswith(".c"):
+                cmd = ["gcc", "-O2", "-fPIC", "-I" + CSRC, "-I" + os.path.join(CSRC, "gen"), "-c", src, "-o", obj]
+            else:
+                cmd = [NVCC] + ARCH + CUFLAGS + ["-I" + CSRC, "-x", "cu" if s.endswith(".cu") else "c++", "-c", src,
+                                               "-o", obj]
+                if not s.endswith(".cu"):
+                    cmd = [NVCC] + ARCH + ["-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I" + CSRC, "-c", src, "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("compile failed: " + " ".join(cmd))
+            if verbose or s.endswith(".cu"):
+                with open(os.path.join(objdir, os.path.basename(s) + ".ptxas.log"), "w") as f:
+                    f.write(r.stdout + r.stderr)
+            relink = True
+    if relink:
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose=True))

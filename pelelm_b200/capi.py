@@ -1,0 +1,204 @@
+"""ctypes binding of libplmchem.so (include/plm_chem.h) -- the same C ABI a C++/Fortran caller links.
+
+`Reactor` mirrors the reference operator (PelePhysics/Reactions/ReactorBase.H:15-98): create by name, `init`,
+`set_typ_vals_ode`, `react(box, rY, rYsrc, T, rEner, rEner_src, FC, mask, dt_react, time)`, `close`.
+Arrays may be numpy arrays (host: staged by the library) or torch CUDA tensors (device pointers are passed
+through unchanged). There is no CPU fallback: loading fails loudly if the library or a B200-class GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libplmchem.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+class A4D(C.Structure):
+    _fields_ = [("p", c_dp), ("jstride", C.c_int64), ("kstride", C.c_int64), ("nstride", C.c_int64),
+                ("lo", C.c_int * 3), ("hi", C.c_int * 3), ("ncomp", C.c_int)]
+
+
+class A4I(C.Structure):
+    _fields_ = [("p", c_ip), ("jstride", C.c_int64), ("kstride", C.c_int64), ("nstride", C.c_int64),
+                ("lo", C.c_int * 3), ("hi", C.c_int * 3), ("ncomp", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ncells", C.c_int64), ("nskipped", C.c_int64), ("nst", C.c_int64), ("nfe", C.c_int64),
+                ("nje", C.c_int64), ("nsetups", C.c_int64), ("nni", C.c_int64), ("ncfn", C.c_int64),
+                ("netf", C.c_int64), ("nfailed", C.c_int64), ("max_fc", C.c_int64), ("min_fc", C.c_int64),
+                ("kernel_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals", "plm_react_box", "plm_react_flat",
+           "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
+           "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack"]
+
+_lib = None
+
+
+def load():
+    """Load libplmchem.so and declare the prototypes. Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise RuntimeError("libplmchem.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIBPATH)
+    vp = C.c_void_p
+    L.plm_reactor_create.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p]
+    L.plm_reactor_init.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                   C.c_int, C.c_int, C.c_int]
+    L.plm_reactor_set_typ_vals.argtypes = [vp, c_dp, C.c_int]
+    L.plm_react_box.argtypes = [vp, c_ip, c_ip, A4D, A4D, A4D, A4D, A4D, A4D, A4I, c_dp, c_dp, vp]
+    L.plm_react_flat.argtypes = [vp, vp, vp, vp, vp, c_dp, c_dp, C.c_int, vp]
+    L.plm_reactor_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.plm_reactor_cell_status.argtypes = [vp, vp, C.c_int64]
+    L.plm_reactor_close.argtypes = [vp]
+    L.plm_reactor_close.restype = None
+    L.plm_num_species.argtypes = [vp]
+    L.plm_last_error.restype = C.c_char_p
+    L.plm_eval_rhs.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp, vp, vp]
+    L.plm_eval_jac.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.plm_box_costs.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.plm_knapsack.argtypes = [C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_ip, c_dp]
+    _lib = L
+    return L
+
+
+class PlmError(RuntimeError):
+    pass
+
+
+def _ptr(x):
+    """Raw address of a numpy array or torch tensor (float64/int32, contiguous)."""
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+def knapsack(wgts, nranks, max_efficiency=0.9, do_full=True, nmax=2 ** 31 - 1):
+    """DistributionMapping::KnapSackProcessorMap on a cost vector (host only; needs no GPU)."""
+    L = load()
+    w = (C.c_int64 * len(wgts))(*[int(v) for v in wgts])
+    out = np.zeros(len(wgts), dtype=np.int32)
+    eff = C.c_double(0)
+    rc = L.plm_knapsack(w, len(wgts), nranks, max_efficiency, int(do_full), nmax,
+                        out.ctypes.data_as(c_ip), C.cast(C.byref(eff), c_dp))
+    if rc != 0:
+        raise PlmError("plm_knapsack failed")
+    return out, eff.value
+
+
+class Reactor:
+    """ReactorBase::create(name) + the virtual interface, forwarding to the C ABI."""
+
+    def __init__(self, mechanism: str, chem_integrator: str = "ReactorCvode"):
+        self.L = load()
+        self.h = C.c_void_p()
+        rc = self.L.plm_reactor_create(C.byref(self.h), mechanism.encode(), chem_integrator.encode())
+        if rc != 0:
+            raise PlmError(self.L.plm_last_error().decode())
+        self.mechanism = mechanism
+        self.integrator = chem_integrator
+        self.ns = self.L.plm_num_species(self.h)
+        self.n = self.ns + 1
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PlmError("%d: %s" % (rc, self.L.plm_last_error().decode()))
+
+    def init(self, reactor_type=2, rtol=1e-6, atol=1e-10, max_order=2, max_nls_iters=3, clean_init_massfrac=0,
+             solve_type="denseAJ_direct", rk64=(10, 5, 500)):
+        self._chk(self.L.plm_reactor_init(self.h, reactor_type, rtol, atol, max_order, max_nls_iters,
+                                          clean_init_massfrac, solve_type.encode(), *rk64))
+        return self
+
+    def set_typ_vals_ode(self, typ):
+        typ = np.ascontiguousarray(typ, dtype=np.float64)
+        self._chk(self.L.plm_reactor_set_typ_vals(self.h, typ.ctypes.data_as(c_dp), typ.size))
+
+    @staticmethod
+    def _a4(cls, x, lo, hi, ncomp):
+        nx, ny, nz = hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1
+        a = cls()
+        a.p = C.cast(_ptr(x), c_dp if cls is A4D else c_ip)
+        a.jstride, a.kstride, a.nstride = nx, nx * ny, nx * ny * nz
+        a.lo[:] = lo
+        a.hi[:] = hi
+        a.ncomp = ncomp
+        return a
+
+    def react(self, box_lo, box_hi, rY, rYsrc, T, rEner, rEner_src, FC, mask, dt_react, time=0.0, fab_lo=None,
+              fab_hi=None, stream=None):
+        """In-place on the given arrays (FAB layout: component-major over the FAB box [fab_lo, fab_hi])."""
+        fab_lo = list(box_lo if fab_lo is None else fab_lo)
+        fab_hi = list(box_hi if fab_hi is None else fab_hi)
+        ns = self.ns
+        lo = (C.c_int * 3)(*box_lo)
+        hi = (C.c_int * 3)(*box_hi)
+        a = [self._a4(A4D, rY, fab_lo, fab_hi, ns), self._a4(A4D, rYsrc, fab_lo, fab_hi, ns),
+             self._a4(A4D, T, fab_lo, fab_hi, 1), self._a4(A4D, rEner, fab_lo, fab_hi, 1),
+             self._a4(A4D, rEner_src, fab_lo, fab_hi, 1), self._a4(A4D, FC, fab_lo, fab_hi, 1)]
+        if mask is None:
+            m = A4I()
+        else:
+            m = self._a4(A4I, mask, fab_lo, fab_hi, 1)
+        dt = C.c_double(dt_react)
+        tm = C.c_double(time)
+        self._chk(self.L.plm_react_box(self.h, lo, hi, *a, m, C.cast(C.byref(dt), c_dp), C.cast(C.byref(tm), c_dp),
+                                       C.c_void_p(stream or 0)))
+        return self.stats()
+
+    def react_flat(self, rY, rYsrc, rX, rX_src, dt_react, time=0.0, stream=None):
+        ncells = int(np.prod(rX.shape))
+        dt = C.c_double(dt_react)
+        tm = C.c_double(time)
+        self._chk(self.L.plm_react_flat(self.h, _ptr(rY), _ptr(rYsrc), _ptr(rX), _ptr(rX_src),
+                                        C.cast(C.byref(dt), c_dp), C.cast(C.byref(tm), c_dp), ncells,
+                                        C.c_void_p(stream or 0)))
+        return self.stats()
+
+    def stats(self):
+        s = Stats()
+        self._chk(self.L.plm_reactor_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def cell_status(self, ncells):
+        out = np.zeros(ncells, dtype=np.int32)
+        self._chk(self.L.plm_reactor_cell_status(self.h, out.ctypes.data, ncells))
+        return out
+
+    def eval_rhs(self, y, rhoe, rhoesrc, rYsrc, t=0.0):
+        ydot = np.zeros_like(y) if isinstance(y, np.ndarray) else y.new_zeros(y.shape)
+        self._chk(self.L.plm_eval_rhs(self.h, y.shape[0], t, _ptr(y), _ptr(rhoe), _ptr(rhoesrc), _ptr(rYsrc),
+                                      _ptr(ydot), None))
+        return ydot
+
+    def eval_jac(self, y):
+        n = self.n
+        J = np.zeros((y.shape[0], n * n)) if isinstance(y, np.ndarray) else y.new_zeros((y.shape[0], n * n))
+        self._chk(self.L.plm_eval_jac(self.h, y.shape[0], _ptr(y), _ptr(J), None))
+        return J
+
+    def close(self):
+        if self.h:
+            self.L.plm_reactor_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,880 @@
+// Per-cell variable-order (1..5) variable-step BDF integrator with modified Newton and dense LU,
+// one warp per cell: state vectors are lane-resident (component i = lane + 32*slot), the Nordsieck
+// array, the Newton matrix and its saved Jacobian live in the warp's shared memory, all step-size /
+// order decisions are taken on warp-uniform scalars (butterfly reductions give every lane the same bits).
+//
+// Behavioural specification = SUNDIALS CVODE 6.2.0 as configured by PelePhysics' CPU ReactorCvode
+// (constants cvode_impl.h:57-130, cvode.c:111-118, cvode_nls.c:29-31,
+// cvode_ls_impl.h:40-42). Function names below name the CVODE routine whose decisions they reproduce:
+//   CVode cvode.c:990-1476 | cvHin :1945 | cvStep :2143 | cvAdjustParams/IncreaseBDF/DecreaseBDF :2265-2451
+//   cvRescale :2457 | cvPredict :2485 | cvSetBDF/cvSetTqBDF :2691-2779 | cvNls :2781 | cvHandleNFlag :2954
+//   cvRestore :3008 | cvDoErrorTest :3048 | cvCompleteStep :3162 | cvPrepareNextStep :3218 | cvSetEta :3262
+//   cvComputeEtaqm1/qp1 :3299/:3318 | cvChooseEta :3347 | CVodeGetDky :1490
+//   SUNNonlinSolSolve_Newton sunnonlinsol_newton.c:187 | cvNlsConvTest/Residual/LSetup cvode_nls.c:251-388
+//   cvLsSetup/cvLsLinSys/cvLsSolve cvode_ls.c:1270-1720 | denseGETRF/GETRS sundials_dense.c:135-232
+#pragma once
+#include <cfloat>
+
+#include "chem_warp.cuh"
+
+namespace plm {
+
+struct BdfOpts {
+  double rtol, atol;
+  int qmax;      // cvode.max_order
+  int maxcor;    // ode.max_nls_iters
+  int ajac;      // 1 analytic Jacobian (denseAJ_direct), 0 difference quotient (dense_direct)
+  int use_typ;   // atol_i = typ_i * atol
+  int mxstep;    // 10000 (ReactorCvode.cpp:276)
+  int maxnef;    // 100   (ReactorCvode.cpp:267)
+  int msbj;      // 100   (ReactorCvode.cpp:285)
+};
+
+struct CellStats {
+  int nst, nfe, nje, nsetups, nni, ncfn, netf, flag;
+};
+
+namespace cvc {  // CVODE constants
+constexpr double ETA_MIN_FX = 0.0, ETA_MAX_FX = 1.5, ETA_MAX_FS = 10000.0, ETA_MAX_ES = 10.0, ETA_MAX_GS = 10.0,
+                 ETA_MIN = 0.1, ETA_MAX_EF = 0.2, ETA_MIN_EF = 0.1, ETA_CF = 0.25, ADDON = 0.000001, BIAS1 = 6.0,
+                 BIAS2 = 6.0, BIAS3 = 10.0, HLB_FACTOR = 100.0, HUB_FACTOR = 0.1, H_BIAS = 0.5, CORTES = 0.1,
+                 CRDOWN = 0.3, RDIV = 2.0, DGMAX_LSETUP = 0.3, DGMAX_JBAD = 0.2;
+constexpr int SMALL_NST = 10, SMALL_NEF = 2, LONG_WAIT = 10, MXNCF = 10, MXNEF1 = 3, MAX_ITERS = 4, MSBP = 20;
+constexpr int CV_TOO_MUCH_WORK = -1, CV_TOO_MUCH_ACC = -2, CV_ERR_FAILURE = -3, CV_CONV_FAILURE = -4,
+              CV_ILL_INPUT = -22, CV_TOO_CLOSE = -27;
+enum { DO_ERROR_TEST = 2, PREDICT_AGAIN = 3, TRY_AGAIN = 5 };
+enum { FIRST_CALL = 6, PREV_CONV_FAIL = 7, PREV_ERR_FAIL = 8 };
+enum { NO_FAILURES = 0, FAIL_BAD_J = 1, FAIL_OTHER = 2 };
+enum { NLS_SUCCESS = 0, NLS_CONV_RECVR = 902 };
+}  // namespace cvc
+
+// SUNRpowerR (sundials_math.c:56): pow(base, e) for base > 0 else 0; exp(e*log(base)) keeps the device code call-free
+__device__ __forceinline__ double rpowR(double base, double e) { return base <= 0.0 ? 0.0 : exp(e * log(base)); }
+__device__ __forceinline__ double rpowI(double base, int e)
+{
+  double prod = 1.0;
+  const int expt = e < 0 ? -e : e;
+  for (int i = 1; i <= expt; i++) prod *= base;
+  if (e < 0) prod = 1.0 / prod;
+  return prod;
+}
+
+// ---- dense LU with partial pivoting on the warp's shared-memory matrix (row-major, lane = row) ----
+template <int NSLOT>
+__device__ __forceinline__ int getrf_warp(double* A, int n, int ld, int* perm, int lane)
+{
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s)
+    if (lane + 32 * s < n) perm[lane + 32 * s] = lane + 32 * s;
+  __syncwarp();
+  for (int k = 0; k < n; ++k) {
+    double v = -1.0;
+    int idx = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int i = lane + 32 * s;
+      if (i >= k && i < n) {
+        const double a = fabs(A[i * ld + k]);
+        if (a > v) {  // strict: first occurrence wins (sundials_dense.c:150-152)
+          v = a;
+          idx = i;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(kFull, v, o);
+      const int oi = __shfl_xor_sync(kFull, idx, o);
+      if (ov > v || (ov == v && oi < idx)) {
+        v = ov;
+        idx = oi;
+      }
+    }
+    const int l = idx;
+    if (v == 0.0) return k + 1;
+    if (l != k) {
+      for (int j = lane; j < n; j += 32) {
+        const double t = A[l * ld + j];
+        A[l * ld + j] = A[k * ld + j];
+        A[k * ld + j] = t;
+      }
+      if (lane == 0) {
+        const int t = perm[l];
+        perm[l] = perm[k];
+        perm[k] = t;
+      }
+      __syncwarp();
+    }
+    const double mult = 1.0 / A[k * ld + k];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int i = lane + 32 * s;
+      if (i > k && i < n) {
+        double* row = A + i * ld;
+        const double* rk = A + k * ld;
+        const double mi = row[k] * mult;
+        row[k] = mi;
+        for (int j = k + 1; j < n; ++j) {
+          const double a_kj = rk[j];
+          row[j] -= a_kj * mi;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  return 0;
+}
+
+template <int NSLOT>
+__device__ __forceinline__ double bcast_comp(const double (&b)[NSLOT], int k)
+{
+  double v = b[0];
+#pragma unroll
+  for (int s = 1; s < NSLOT; ++s)
+    if ((k >> 5) == s) v = b[s];
+  return __shfl_sync(kFull, v, k & 31);
+}
+
+// b <- A^{-1} b with the factors of getrf_warp; scratch holds >= n doubles of shared memory
+template <int NSLOT>
+__device__ __forceinline__ void getrs_warp(const double* A, int n, int ld, const int* perm, double (&b)[NSLOT],
+                                           double* scratch, int lane)
+{
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s)
+    if (lane + 32 * s < n) scratch[lane + 32 * s] = b[s];
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s)
+    if (lane + 32 * s < n) b[s] = scratch[perm[lane + 32 * s]];
+  for (int k = 0; k < n - 1; ++k) {
+    const double bk = bcast_comp<NSLOT>(b, k);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int i = lane + 32 * s;
+      if (i > k && i < n) b[s] -= A[i * ld + k] * bk;
+    }
+  }
+  for (int k = n - 1; k > 0; --k) {
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+      if (lane + 32 * s == k) b[s] /= A[k * ld + k];
+    const double bk = bcast_comp<NSLOT>(b, k);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int i = lane + 32 * s;
+      if (i < k) b[s] -= A[i * ld + k] * bk;
+    }
+  }
+  if (lane == 0) b[0] /= A[0];
+  __syncwarp();
+}
+
+template <int NSLOT>
+struct BdfWarp {
+  const DevMech& m;
+  const WarpMem& wm;
+  const BdfOpts& o;
+  const int lane;
+  const int n, P;
+  double rhoe_init, rhoesrc;
+  double src[NSLOT], atolv[NSLOT];
+  double ewt[NSLOT], acor[NSLOT], yv[NSLOT], ft[NSLOT], dl[NSLOT], tv[NSLOT];
+  double tn, h, hprime, hscale, eta, etamax;
+  int q, qprime, L, qwait, indx_acor;
+  double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
+  int nst, nfe, ncfn, netf, nni, nsetups, nje, nstlp, nstlj;
+  int jcur, convfail;
+
+  __device__ BdfWarp(const DevMech& m_, const WarpMem& wm_, const BdfOpts& o_, int lane_)
+      : m(m_), wm(wm_), o(o_), lane(lane_), n(m_.n), P(m_.nsp_pad)
+  {
+  }
+
+  __device__ __forceinline__ bool valid(int s) const { return lane + 32 * s < n; }
+  __device__ __forceinline__ double& zn(int j, int s) const { return wm.zn[j * P + lane + 32 * s]; }
+  __device__ __forceinline__ double& tau(int i) const { return wm.sm[i]; }
+  __device__ __forceinline__ double& tq(int i) const { return wm.sm[8 + i]; }
+  __device__ __forceinline__ double& l(int i) const { return wm.sm[16 + i]; }
+
+  __device__ __forceinline__ double wrms(const double (&x)[NSLOT], const double (&w)[NSLOT]) const
+  {
+    double a = 0.0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+      if (valid(s)) {
+        const double p = x[s] * w[s];
+        a += p * p;
+      }
+    return sqrt(warp_sum(a) / n);
+  }
+  __device__ __forceinline__ double wrms_zn(int j) const
+  {
+    double a = 0.0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+      if (valid(s)) {
+        const double p = zn(j, s) * ewt[s];
+        a += p * p;
+      }
+    return sqrt(warp_sum(a) / n);
+  }
+  // cvEwtSetSV on zn[0]; false if a weight is non-positive
+  __device__ __forceinline__ bool ewtset()
+  {
+    int bad = 0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      ewt[s] = 1.0;
+      if (valid(s)) {
+        const double t = o.rtol * fabs(zn(0, s)) + atolv[s];
+        if (t <= 0.0) bad = 1;
+        ewt[s] = 1.0 / t;
+      }
+    }
+    return __any_sync(kFull, bad) == 0;
+  }
+  __device__ __forceinline__ void f(double t, const double (&y)[NSLOT], double (&ydot)[NSLOT])
+  {
+    rhs_warp<NSLOT>(m, wm, lane, t, y, src, rhoe_init, rhoesrc, ydot);
+    nfe++;
+  }
+
+  // cvLsDenseDQJac (cvode_ls.c:1034-1107): fy = f(tn, yv) in ft
+  __device__ __forceinline__ void dq_jac(double* Jm)
+  {
+    const int ld = wm.ld;
+    const double uround = DBL_EPSILON, srur = sqrt(uround);
+    const double fnorm = wrms(ft, ewt);
+    const double minInc = (fnorm != 0.0) ? (1000.0 * fabs(h) * uround * n * fnorm) : 1.0;
+    double ysave[NSLOT], ft2[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) ysave[s] = yv[s];
+    for (int j = 0; j < n; ++j) {
+      double inc_l = 0.0;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (lane + 32 * s == j) {
+          inc_l = fmax(srur * fabs(ysave[s]), minInc / ewt[s]);
+          yv[s] += inc_l;
+        }
+      const double inc = __shfl_sync(kFull, inc_l, j & 31);
+      rhs_warp<NSLOT>(m, wm, lane, tn, yv, src, rhoe_init, rhoesrc, ft2);
+      nfe++;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) yv[s] = ysave[s];
+      const double inc_inv = 1.0 / inc;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) Jm[(lane + 32 * s) * ld + j] = inc_inv * ft2[s] - inc_inv * ft[s];
+    }
+    __syncwarp();
+  }
+
+  // cvNlsLSetup + cvLsSetup + cvLsLinSys + dense factorisation
+  __device__ __forceinline__ int lsetup()
+  {
+    const int ld = wm.ld;
+    const double dgamma = fabs((gamma / gammap) - 1.0);
+    const bool jbad = (nst == 0) || (nst >= nstlj + o.msbj) ||
+                      ((convfail == cvc::FAIL_BAD_J) && (dgamma < cvc::DGMAX_JBAD)) || (convfail == cvc::FAIL_OTHER);
+    __syncwarp();
+    if (jbad) {
+      jcur = 1;
+      if (o.ajac) jac_warp<NSLOT>(m, wm, lane, yv, wm.A);
+      else dq_jac(wm.A);
+      for (int e = lane; e < n * ld; e += 32) wm.J[e] = wm.A[e];
+      nje++;
+      nstlj = nst;
+    } else {
+      jcur = 0;
+      for (int e = lane; e < n * ld; e += 32) wm.A[e] = wm.J[e];
+    }
+    __syncwarp();
+    const double c = -gamma;
+    for (int e = lane; e < n * ld; e += 32) {
+      const int i = e / ld, j = e - i * ld;
+      double a = wm.A[e] * c;
+      if (i == j) a += 1.0;
+      wm.A[e] = a;
+    }
+    __syncwarp();
+    const int ier = getrf_warp<NSLOT>(wm.A, n, ld, wm.perm, lane);
+    nsetups++;
+    gamrat = 1.0;
+    gammap = gamma;
+    crate = 1.0;
+    nstlp = nst;
+    return ier > 0 ? cvc::NLS_CONV_RECVR : cvc::NLS_SUCCESS;
+  }
+
+  // cvNlsResidual: res = rl1*zn[1] + acor - gamma*f(tn, zn[0]+acor)   (into dl)
+  __device__ __forceinline__ void residual()
+  {
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) yv[s] = valid(s) ? zn(0, s) + acor[s] : 0.0;
+    f(tn, yv, ft);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+      if (valid(s)) {
+        const double r = rl1 * zn(1, s) + acor[s];
+        dl[s] = -gamma * ft[s] + r;
+      } else {
+        dl[s] = 0.0;
+      }
+  }
+
+  __device__ __forceinline__ int newton(bool callSetup)
+  {
+    bool jbadflag = false;
+    int nls_jcur = 0, retval;
+    for (;;) {
+      residual();
+      retval = cvc::NLS_SUCCESS;
+      if (callSetup) {
+        if (jbadflag) convfail = cvc::FAIL_BAD_J;
+        retval = lsetup();
+        nls_jcur = jcur;
+        if (retval != cvc::NLS_SUCCESS) return retval;
+      }
+      int mit = 0;
+      for (;;) {
+        nni++;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) dl[s] = -dl[s];
+        getrs_warp<NSLOT>(wm.A, n, wm.ld, wm.perm, dl, wm.q, lane);
+        if (gamrat != 1.0) {
+          const double sc = 2.0 / (1.0 + gamrat);
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s) dl[s] *= sc;
+        }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) acor[s] = valid(s) ? acor[s] + dl[s] : 0.0;
+        const double del = wrms(dl, ewt);
+        if (mit > 0) crate = fmax(cvc::CRDOWN * crate, del / delp);
+        const double dcon = del * fmin(1.0, crate) / tq(4);
+        if (dcon <= 1.0) {
+          acnrm = (mit == 0) ? del : wrms(acor, ewt);
+          return cvc::NLS_SUCCESS;
+        }
+        if ((mit >= 1) && (del > cvc::RDIV * delp)) {
+          retval = cvc::NLS_CONV_RECVR;
+          break;
+        }
+        delp = del;
+        mit++;
+        if (mit >= o.maxcor) {
+          retval = cvc::NLS_CONV_RECVR;
+          break;
+        }
+        residual();
+      }
+      if ((retval > 0) && !nls_jcur) {
+        callSetup = true;
+        jbadflag = true;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) acor[s] = 0.0;
+        continue;
+      }
+      break;
+    }
+    return retval;
+  }
+
+  __device__ __forceinline__ void rescale()
+  {
+    double fac = eta;
+    for (int j = 1; j <= q; j++) {
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) zn(j, s) *= fac;
+      fac = eta * fac;
+    }
+    h = hscale * eta;
+    hscale = h;
+  }
+
+  __device__ __forceinline__ void increase_bdf()
+  {
+    __syncwarp();
+    if (lane == 0) {  // scalar recurrences are done by one lane on the shared coefficient arrays
+      double alpha0, alpha1, prod, xi, xiold, hsum;
+      for (int i = 0; i <= o.qmax; i++) l(i) = 0.0;
+      l(2) = alpha1 = prod = xiold = 1.0;
+      alpha0 = -1.0;
+      hsum = hscale;
+      if (q > 1) {
+        for (int j = 1; j < q; j++) {
+          hsum += tau(j + 1);
+          xi = hsum / hscale;
+          prod *= xi;
+          alpha0 -= 1.0 / (j + 1);
+          alpha1 += 1.0 / xi;
+          for (int i = j + 2; i >= 2; i--) l(i) = l(i) * xiold + l(i - 1);
+          xiold = xi;
+        }
+      }
+      wm.sm[24] = (-alpha0 - alpha1) / prod;
+    }
+    __syncwarp();
+    const double A1 = wm.sm[24];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+      if (valid(s)) zn(L, s) = A1 * zn(indx_acor, s);
+    if (q > 1)
+      for (int j = 2; j <= q; j++) {
+        const double lj = l(j);
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (valid(s)) zn(j, s) = lj * zn(L, s) + zn(j, s);
+      }
+  }
+  __device__ __forceinline__ void decrease_bdf()
+  {
+    __syncwarp();
+    if (lane == 0) {
+      double hsum, xi;
+      for (int i = 0; i <= o.qmax; i++) l(i) = 0.0;
+      l(2) = 1.0;
+      hsum = 0.0;
+      for (int j = 1; j <= q - 2; j++) {
+        hsum += tau(j);
+        xi = hsum / hscale;
+        for (int i = j + 2; i >= 2; i--) l(i) = l(i) * xi + l(i - 1);
+      }
+    }
+    __syncwarp();
+    if (q > 2)
+      for (int j = 2; j < q; j++) {
+        const double lj = l(j);
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (valid(s)) zn(j, s) = -lj * zn(q, s) + zn(j, s);
+      }
+  }
+  __device__ __forceinline__ void adjust_order(int deltaq)
+  {
+    if ((q == 2) && (deltaq != 1)) return;
+    if (deltaq == 1) increase_bdf();
+    else if (deltaq == -1) decrease_bdf();
+  }
+  __device__ __forceinline__ void adjust_params()
+  {
+    if (qprime != q) {
+      adjust_order(qprime - q);
+      q = qprime;
+      L = q + 1;
+      qwait = L;
+    }
+    rescale();
+  }
+  __device__ __forceinline__ void predict()
+  {
+    tn += h;
+    for (int k = 1; k <= q; k++)
+      for (int j = q; j >= k; j--) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (valid(s)) zn(j - 1, s) = zn(j - 1, s) + zn(j, s);
+      }
+  }
+  __device__ __forceinline__ void restore(double saved_t)
+  {
+    tn = saved_t;
+    for (int k = 1; k <= q; k++)
+      for (int j = q; j >= k; j--) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (valid(s)) zn(j - 1, s) = zn(j - 1, s) - zn(j, s);
+      }
+  }
+  __device__ __forceinline__ void set_bdf()
+  {
+    __syncwarp();
+    if (lane == 0) {
+      double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
+      l(0) = l(1) = xi_inv = xistar_inv = 1.0;
+      for (int i = 2; i <= q; i++) l(i) = 0.0;
+      alpha0 = alpha0_hat = -1.0;
+      hsum = h;
+      if (q > 1) {
+        for (int j = 2; j < q; j++) {
+          hsum += tau(j - 1);
+          xi_inv = h / hsum;
+          alpha0 -= 1.0 / j;
+          for (int i = j; i >= 1; i--) l(i) += l(i - 1) * xi_inv;
+        }
+        alpha0 -= 1.0 / q;
+        xistar_inv = -l(1) - alpha0;
+        hsum += tau(q - 1);
+        xi_inv = h / hsum;
+        alpha0_hat = -l(1) - xi_inv;
+        for (int i = q; i >= 1; i--) l(i) += l(i - 1) * xistar_inv;
+      }
+      const double A1 = 1.0 - alpha0_hat + alpha0;
+      const double A2 = 1.0 + q * A1;
+      tq(2) = fabs(A1 / (alpha0 * A2));
+      tq(5) = fabs(A2 * xistar_inv / (l(q) * xi_inv));
+      if (qwait == 1) {
+        if (q > 1) {
+          const double C = xistar_inv / l(q);
+          const double A3 = alpha0 + 1.0 / q;
+          const double A4 = alpha0_hat + xi_inv;
+          const double Cpinv = (1.0 - A4 + A3) / A3;
+          tq(1) = fabs(C * Cpinv);
+        } else
+          tq(1) = 1.0;
+        hsum += tau(q);
+        xi_inv = h / hsum;
+        const double A5 = alpha0 - (1.0 / (q + 1));
+        const double A6 = alpha0_hat - xi_inv;
+        const double Cppinv = (1.0 - A6 + A5) / A2;
+        tq(3) = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+      }
+      tq(4) = cvc::CORTES / tq(2);
+    }
+    __syncwarp();
+    rl1 = 1.0 / l(1);
+    gamma = h * rl1;
+    if (nst == 0) gammap = gamma;
+    gamrat = (nst > 0) ? gamma / gammap : 1.0;
+  }
+
+  __device__ __forceinline__ int nls(int nflag)
+  {
+    convfail = ((nflag == cvc::FIRST_CALL) || (nflag == cvc::PREV_ERR_FAIL)) ? cvc::NO_FAILURES : cvc::FAIL_OTHER;
+    const bool callSetup = (nflag == cvc::PREV_CONV_FAIL) || (nflag == cvc::PREV_ERR_FAIL) || (nst == 0) ||
+                           (nst >= nstlp + cvc::MSBP) || (fabs(gamrat - 1.0) > cvc::DGMAX_LSETUP);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) acor[s] = 0.0;
+    const int flag = newton(callSetup);
+    if (flag != cvc::NLS_SUCCESS) return flag;
+    jcur = 0;
+    return 0;
+  }
+
+  __device__ __forceinline__ int handle_nflag(int& nflag, double saved_t, int& ncf)
+  {
+    if (nflag == 0) return cvc::DO_ERROR_TEST;
+    ncfn++;
+    restore(saved_t);
+    ncf++;
+    etamax = 1.0;
+    if (ncf == cvc::MXNCF) return cvc::CV_CONV_FAILURE;
+    eta = cvc::ETA_CF;
+    nflag = cvc::PREV_CONV_FAIL;
+    rescale();
+    return cvc::PREDICT_AGAIN;
+  }
+
+  __device__ __forceinline__ int do_error_test(int& nflag, double saved_t, int& nef, double& dsm)
+  {
+    dsm = acnrm * tq(2);
+    if (dsm <= 1.0) return 0;
+    nef++;
+    netf++;
+    nflag = cvc::PREV_ERR_FAIL;
+    restore(saved_t);
+    if (nef == o.maxnef) return cvc::CV_ERR_FAILURE;
+    etamax = 1.0;
+    if (nef <= cvc::MXNEF1) {
+      eta = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L) + cvc::ADDON);
+      eta = fmax(cvc::ETA_MIN_EF, eta);
+      if (nef >= cvc::SMALL_NEF) eta = fmin(eta, cvc::ETA_MAX_EF);
+      rescale();
+      return cvc::TRY_AGAIN;
+    }
+    if (q > 1) {
+      eta = cvc::ETA_MIN_EF;
+      adjust_order(-1);
+      L = q;
+      q--;
+      qwait = L;
+      rescale();
+      return cvc::TRY_AGAIN;
+    }
+    eta = cvc::ETA_MIN_EF;
+    h *= eta;
+    hscale = h;
+    qwait = cvc::LONG_WAIT;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) yv[s] = valid(s) ? zn(0, s) : 0.0;
+    f(tn, yv, tv);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+      if (valid(s)) zn(1, s) = h * tv[s];
+    return cvc::TRY_AGAIN;
+  }
+
+  __device__ __forceinline__ void complete_step()
+  {
+    nst++;
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = q; i >= 2; i--) tau(i) = tau(i - 1);
+      if ((q == 1) && (nst > 1)) tau(2) = tau(1);
+      tau(1) = h;
+    }
+    __syncwarp();
+    for (int j = 0; j <= q; j++) {
+      const double lj = l(j);
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) zn(j, s) = lj * acor[s] + zn(j, s);
+    }
+    qwait--;
+    if ((qwait == 1) && (q != o.qmax)) {
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) zn(o.qmax, s) = acor[s];
+      saved_tq5 = tq(5);
+      indx_acor = o.qmax;
+    }
+  }
+
+  __device__ __forceinline__ void set_eta()
+  {
+    if ((eta > cvc::ETA_MIN_FX) && (eta < cvc::ETA_MAX_FX)) {
+      eta = 1.0;
+      hprime = h;
+    } else {
+      if (eta >= cvc::ETA_MAX_FX) eta = fmin(eta, etamax);
+      else eta = fmax(eta, cvc::ETA_MIN);
+      hprime = h * eta;
+    }
+  }
+
+  __device__ __forceinline__ void prepare_next_step(double dsm)
+  {
+    if (etamax == 1.0) {
+      qwait = max(qwait, 2);
+      qprime = q;
+      hprime = h;
+      eta = 1.0;
+      return;
+    }
+    const double etaq = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L) + cvc::ADDON);
+    if (qwait != 0) {
+      eta = etaq;
+      qprime = q;
+      set_eta();
+      return;
+    }
+    qwait = 2;
+    double etaqm1 = 0.0, etaqp1 = 0.0;
+    if (q > 1) {
+      const double ddn = wrms_zn(q) * tq(1);
+      etaqm1 = 1.0 / (rpowR(cvc::BIAS1 * ddn, 1.0 / q) + cvc::ADDON);
+    }
+    if (q != o.qmax && saved_tq5 != 0.0) {
+      const double cquot = (tq(5) / saved_tq5) * rpowI(h / tau(2), L);
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) tv[s] = valid(s) ? -cquot * zn(o.qmax, s) + acor[s] : 0.0;
+      const double dup = wrms(tv, ewt) * tq(3);
+      etaqp1 = 1.0 / (rpowR(cvc::BIAS3 * dup, 1.0 / (L + 1)) + cvc::ADDON);
+    }
+    const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
+    if ((etam > cvc::ETA_MIN_FX) && (etam < cvc::ETA_MAX_FX)) {
+      eta = 1.0;
+      qprime = q;
+    } else if (etam == etaq) {
+      eta = etaq;
+      qprime = q;
+    } else if (etam == etaqm1) {
+      eta = etaqm1;
+      qprime = q - 1;
+    } else {
+      eta = etaqp1;
+      qprime = q + 1;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) zn(o.qmax, s) = acor[s];
+    }
+    set_eta();
+  }
+
+  __device__ __forceinline__ int step()
+  {
+    int ncf = 0, nef = 0, nflag, kflag, eflag;
+    double dsm = 0.0;
+    if ((nst > 0) && (hprime != h)) adjust_params();
+    const double saved_t = tn;
+    nflag = cvc::FIRST_CALL;
+    for (;;) {
+      predict();
+      set_bdf();
+      nflag = nls(nflag);
+      kflag = handle_nflag(nflag, saved_t, ncf);
+      if (kflag == cvc::PREDICT_AGAIN) continue;
+      if (kflag != cvc::DO_ERROR_TEST) return kflag;
+      eflag = do_error_test(nflag, saved_t, nef, dsm);
+      if (eflag == cvc::TRY_AGAIN) continue;
+      if (eflag != 0) return eflag;
+      break;
+    }
+    complete_step();
+    prepare_next_step(dsm);
+    etamax = (nst <= cvc::SMALL_NST) ? cvc::ETA_MAX_ES : cvc::ETA_MAX_GS;
+    const double t2 = tq(2);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) acor[s] *= t2;
+    return 0;
+  }
+
+  __device__ __forceinline__ int hin(double tout)
+  {
+    const double uround = DBL_EPSILON;
+    const double tdiff = tout - tn;
+    if (tdiff == 0.0) return cvc::CV_TOO_CLOSE;
+    const int sign = (tdiff > 0.0) ? 1 : -1;
+    const double tdist = fabs(tdiff);
+    const double tround = uround * fmax(fabs(tn), fabs(tout));
+    if (tdist < 2.0 * tround) return cvc::CV_TOO_CLOSE;
+    const double hlb = cvc::HLB_FACTOR * tround;
+    // cvUpperBoundH0
+    double hub_inv_l = 0.0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+      if (valid(s)) {
+        const double t1 = cvc::HUB_FACTOR * fabs(zn(0, s)) + 1.0 / ewt[s];
+        hub_inv_l = fmax(hub_inv_l, fabs(zn(1, s)) / t1);
+      }
+    const double hub_inv = warp_max(hub_inv_l);
+    double hub = cvc::HUB_FACTOR * tdist;
+    if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
+    double hg = sqrt(hlb * hub);
+    if (hub < hlb) {
+      h = (sign == -1) ? -hg : hg;
+      return 0;
+    }
+    double hnew = hg;
+    for (int count1 = 1; count1 <= cvc::MAX_ITERS; count1++) {
+      const double hgs = hg * sign;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) yv[s] = valid(s) ? hgs * zn(1, s) + zn(0, s) : 0.0;
+      f(tn + hgs, yv, tv);
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) tv[s] = valid(s) ? (1.0 / hgs) * (tv[s] - zn(1, s)) : 0.0;
+      const double yddnrm = wrms(tv, ewt);
+      hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
+      if (count1 == cvc::MAX_ITERS) break;
+      const double hrat = hnew / hg;
+      if ((hrat > 0.5) && (hrat < 2.0)) break;
+      if ((count1 > 1) && (hrat > 2.0)) {
+        hnew = hg;
+        break;
+      }
+      hg = hnew;
+    }
+    double h0 = cvc::H_BIAS * hnew;
+    if (h0 < hlb) h0 = hlb;
+    if (h0 > hub) h0 = hub;
+    if (sign == -1) h0 = -h0;
+    h = h0;
+    return 0;
+  }
+
+  // CVodeReInit + CVode(tout, CV_NORMAL). y0 in / result out through yio (lane components).
+  __device__ __forceinline__ int integrate(double (&yio)[NSLOT], double t0, double tout, CellStats& st)
+  {
+    tn = t0;
+    q = 1;
+    L = 2;
+    qwait = L;
+    etamax = cvc::ETA_MAX_FS;
+    nst = nfe = ncfn = netf = nni = nsetups = nje = nstlp = nstlj = 0;
+    saved_tq5 = 0.0;
+    indx_acor = o.qmax;
+    crate = 1.0;
+    delp = 0.0;
+    jcur = 0;
+    convfail = 0;
+    eta = 1.0;
+    qprime = 1;
+    gammap = gamma = gamrat = rl1 = 1.0;
+    acnrm = 0.0;
+    __syncwarp();
+    if (lane < 24) wm.sm[lane] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      acor[s] = 0.0;
+      if (lane + 32 * s < P)
+        for (int j = 0; j <= o.qmax; ++j) zn(j, s) = 0.0;
+      if (valid(s)) zn(0, s) = yio[s];
+    }
+    __syncwarp();
+    int istate = 0;
+    if (!ewtset()) {
+      istate = cvc::CV_ILL_INPUT;
+    } else {
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) yv[s] = valid(s) ? zn(0, s) : 0.0;
+      f(tn, yv, tv);
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) zn(1, s) = tv[s];
+      istate = hin(tout);
+    }
+    if (istate == 0) {
+      hscale = h;
+      hprime = h;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) zn(1, s) *= h;
+      int nstloc = 0;
+      for (;;) {
+        if (nst > 0 && !ewtset()) {
+          istate = cvc::CV_ILL_INPUT;
+          break;
+        }
+        if (nstloc >= o.mxstep) {
+          istate = cvc::CV_TOO_MUCH_WORK;
+          break;
+        }
+        if (DBL_EPSILON * wrms_zn(0) > 1.0) {
+          istate = cvc::CV_TOO_MUCH_ACC;
+          break;
+        }
+        const int kflag = step();
+        if (kflag != 0) {
+          istate = kflag;
+          break;
+        }
+        nstloc++;
+        if ((tn - tout) * h >= 0.0) break;
+      }
+    }
+    if (istate == 0) {
+      // CVodeGetDky(tout, 0): sum_{j=q..0} s^j zn[j]
+      const double sfac = (tout - tn) / h;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        if (valid(s)) {
+          double z = 0.0;
+          for (int j = q; j >= 0; j--) {
+            double c = 1.0;
+            for (int i = 0; i < j; i++) c *= sfac;
+            z = (j == q) ? c * zn(j, s) : z + c * zn(j, s);
+          }
+          yio[s] = z;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) yio[s] = zn(0, s);
+    }
+    st.nst = nst;
+    st.nfe = nfe;
+    st.nje = nje;
+    st.nsetups = nsetups;
+    st.nni = nni;
+    st.ncfn = ncfn;
+    st.netf = netf;
+    st.flag = istate;
+    return istate;
+  }
+};
+
+}  // namespace plm

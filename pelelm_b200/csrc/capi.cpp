@@ -1,0 +1,448 @@
+// C ABI of libplmchem.so (include/plm_chem.h): argument checking, host/device pointer staging,
+// launch configuration, statistics. No chemistry is computed on the host.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/plm_chem.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg)
+{
+  g_err = msg;
+  return code;
+}
+#define PLM_CUDA(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) return fail(PLM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+const plm_mech_tables* find_mech(const char* name)
+{
+  if (!name) return nullptr;
+  if (!std::strcmp(name, "LiDryer")) return &plm_tables_LiDryer;
+  if (!std::strcmp(name, "drm19")) return &plm_tables_drm19;
+  if (!std::strcmp(name, "dodecane_lu")) return &plm_tables_dodecane_lu;
+  return nullptr;
+}
+
+bool is_device_ptr(const void* p)
+{
+  if (!p) return false;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return -1;
+    cap = bytes;
+    return 0;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct plm_reactor {
+  const plm_mech_tables* tables = nullptr;
+  plm::DevMechOwner mech;
+  int integ = plm::kIntegCvode;
+  bool inited = false;
+  plm::ReactOpts opts{};
+  int num_sms = 0;
+  DevBuf ctrl;     // counter (1) + gstats (12) as unsigned long long
+  DevBuf status;   // int per cell
+  DevBuf jglobal;  // saved Jacobians when they do not fit in shared memory
+  DevBuf stage[7]; // host-pointer staging: rY rYsrc T rE rEsrc FC mask
+  DevBuf scratch[6];
+  int64_t last_ncells = 0;
+  plm_stats last{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // cached launch configuration
+  plm::LaunchCfg cfg{};
+  bool j_in_smem = true;
+  int cfg_qmax = -1;
+};
+
+extern "C" {
+
+const char* plm_last_error(void) { return g_err.c_str(); }
+
+int plm_reactor_create(plm_reactor** out, const char* mechanism, const char* integrator)
+{
+  if (!out) return fail(PLM_ERR_ARG, "null output handle");
+  *out = nullptr;
+  const plm_mech_tables* t = find_mech(mechanism);
+  if (!t) return fail(PLM_ERR_MECH, std::string("unknown mechanism '") + (mechanism ? mechanism : "(null)") +
+                                      "'; valid: LiDryer, drm19, dodecane_lu");
+  int integ;
+  if (integrator && !std::strcmp(integrator, "ReactorCvode")) integ = plm::kIntegCvode;
+  else if (integrator && !std::strcmp(integrator, "ReactorRK64")) integ = plm::kIntegRK64;
+  else  // Factory.H:134-150 aborts listing the valid keys
+    return fail(PLM_ERR_ARG, std::string("unknown chem_integrator '") + (integrator ? integrator : "(null)") +
+                               "'; valid: ReactorCvode, ReactorRK64");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(PLM_ERR_NO_DEVICE, "no CUDA device: libplmchem has no CPU path");
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop{};
+  PLM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) return fail(PLM_ERR_NO_DEVICE, "device is not sm_100-class; this library is built for sm_100a only");
+  auto* r = new plm_reactor();
+  r->tables = t;
+  r->integ = integ;
+  r->num_sms = prop.multiProcessorCount;
+  if (plm::build_dev_mech(t, &r->mech) != 0) {
+    delete r;
+    return fail(PLM_ERR_CUDA, "failed to build/upload mechanism tables");
+  }
+  if (r->ctrl.ensure(16 * sizeof(unsigned long long)) != 0) {
+    plm::free_dev_mech(&r->mech);
+    delete r;
+    return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+  }
+  cudaEventCreate(&r->ev0);
+  cudaEventCreate(&r->ev1);
+  *out = r;
+  return PLM_OK;
+}
+
+int plm_num_species(const plm_reactor* r) { return r ? r->tables->ns : 0; }
+
+int plm_reactor_init(plm_reactor* r, int reactor_type, double rtol, double atol, int max_order, int max_nls_iters,
+                     int clean_init_massfrac, const char* solve_type, int rk64_guess, int rk64_min, int rk64_max)
+{
+  if (!r) return fail(PLM_ERR_ARG, "null reactor");
+  if (reactor_type != 2)  // ReactorTypes.H:15-21 accepts 1|2; only the h (HP) reactor PeleLM uses is built
+    return fail(PLM_ERR_ARG, "only reactor_type 2 (h, constant pressure) is implemented");
+  if (!(rtol > 0) || !(atol > 0)) return fail(PLM_ERR_ARG, "rtol/atol must be positive");
+  if (max_order < 1 || max_order > 5) return fail(PLM_ERR_ARG, "cvode.max_order must be in 1..5");
+  if (max_nls_iters < 1) return fail(PLM_ERR_ARG, "ode.max_nls_iters must be >= 1");
+  int ajac = 1;
+  if (solve_type && !std::strcmp(solve_type, "denseAJ_direct")) ajac = 1;
+  else if (solve_type && !std::strcmp(solve_type, "dense_direct")) ajac = 0;
+  else if (r->integ == plm::kIntegCvode)
+    return fail(PLM_ERR_ARG, "cvode.solve_type must be denseAJ_direct or dense_direct (others are out of scope)");
+  if (rk64_guess < 1 || rk64_min < 1 || rk64_max < 1) return fail(PLM_ERR_ARG, "rk64 substep counts must be >= 1");
+  plm::ReactOpts& o = r->opts;
+  const bool had_typ = o.use_typ;
+  o.rtol = rtol;
+  o.atol = atol;
+  o.qmax = max_order;
+  o.maxcor = max_nls_iters;
+  o.ajac = ajac;
+  o.clean_init_massfrac = clean_init_massfrac;
+  o.rk64_guess = rk64_guess;
+  o.rk64_min = rk64_min;
+  o.rk64_max = rk64_max;
+  o.use_typ = had_typ;
+  r->inited = true;
+  r->cfg_qmax = -1;
+  return PLM_OK;
+}
+
+int plm_reactor_set_typ_vals(plm_reactor* r, const double* typ, int n)
+{
+  if (!r || !typ) return fail(PLM_ERR_ARG, "null argument");
+  if (n != r->tables->ns + 1) return fail(PLM_ERR_ARG, "typical values must have NUM_SPECIES+1 entries");
+  for (int i = 0; i < n; ++i) r->opts.typ_vals[i] = typ[i];
+  r->opts.use_typ = typ[0] > 0.0;  // ReactorBase.cpp:105
+  return PLM_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int configure(plm_reactor* r)
+{
+  if (r->cfg_qmax == r->opts.qmax) return PLM_OK;
+  const plm::DevMech& m = r->mech.h;
+  const int qmax = (r->integ == plm::kIntegCvode) ? r->opts.qmax : 0;
+  int best_warps = 0;
+  for (int pass = 0; pass < 2 && best_warps == 0; ++pass) {
+    const bool jsm = (pass == 0);
+    for (int wpb : {4, 2, 1}) {
+      const size_t smem = plm::react_smem_bytes(m, qmax, jsm, wpb);
+      if (smem > 227 * 1024) continue;
+      const int occ = plm::react_occupancy(m, r->integ, wpb * 32, smem);
+      if (occ <= 0) continue;
+      // keeping J in shared memory is only worth it if it does not starve the SM of warps
+      if (jsm && occ * wpb < 8) continue;
+      if (occ * wpb > best_warps) {
+        best_warps = occ * wpb;
+        r->cfg.blocks = occ * r->num_sms;
+        r->cfg.threads = wpb * 32;
+        r->cfg.smem_bytes = smem;
+        r->j_in_smem = jsm;
+      }
+    }
+  }
+  if (best_warps == 0) return fail(PLM_ERR_CUDA, "no launch configuration fits in shared memory");
+  if (!r->j_in_smem) {
+    const size_t nw = size_t(r->cfg.blocks) * (r->cfg.threads / 32);
+    if (r->jglobal.ensure(nw * m.n * plm::ld_for(m) * sizeof(double)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+  }
+  r->cfg_qmax = r->opts.qmax;
+  return PLM_OK;
+}
+
+int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
+{
+  int rc = configure(r);
+  if (rc != PLM_OK) return rc;
+  a.ld = plm::ld_for(r->mech.h);
+  if (r->status.ensure(std::max<int64_t>(a.ncells, 1) * sizeof(int)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+  auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
+  unsigned long long init[16] = {0};
+  init[1 + 11] = ~0ull;  // min_fc
+  PLM_CUDA(cudaMemcpyAsync(ctrl, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  plm::LaunchCfg cfg = r->cfg;
+  const int64_t warps_needed = (a.ncells + plm::kCellsPerGrab - 1) / plm::kCellsPerGrab;
+  const int wpb = cfg.threads / 32;
+  cfg.blocks = int(std::max<int64_t>(1, std::min<int64_t>(cfg.blocks, (warps_needed + wpb - 1) / wpb)));
+  PLM_CUDA(cudaEventRecord(r->ev0, stream));
+  PLM_CUDA(plm::launch_react(r->mech.h, r->opts, a, cfg, r->integ, ctrl, ctrl + 1, static_cast<int*>(r->status.p),
+                             r->j_in_smem ? nullptr : static_cast<double*>(r->jglobal.p), stream));
+  PLM_CUDA(cudaEventRecord(r->ev1, stream));
+  unsigned long long host[16];
+  PLM_CUDA(cudaMemcpyAsync(host, ctrl, sizeof(host), cudaMemcpyDeviceToHost, stream));
+  PLM_CUDA(cudaStreamSynchronize(stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, r->ev0, r->ev1);
+  const unsigned long long* g = host + 1;
+  plm_stats& s = r->last;
+  s.nst = int64_t(g[0]); s.nfe = int64_t(g[1]); s.nje = int64_t(g[2]); s.nsetups = int64_t(g[3]);
+  s.nni = int64_t(g[4]); s.ncfn = int64_t(g[5]); s.netf = int64_t(g[6]); s.nfailed = int64_t(g[7]);
+  s.nskipped = int64_t(g[8]); s.ncells = int64_t(g[9]);
+  s.max_fc = int64_t(g[10]); s.min_fc = (g[9] ? int64_t(g[11]) : 0);
+  s.kernel_ms = ms;
+  r->last_ncells = a.ncells;
+  return PLM_OK;
+}
+
+// copy a host FAB view to the device; returns device pointer in *dp
+template <class T>
+int stage_in(DevBuf& buf, const T* host, size_t count, T** dp, cudaStream_t st, bool copy)
+{
+  if (buf.ensure(std::max<size_t>(count, 1) * sizeof(T)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+  *dp = static_cast<T*>(buf.p);
+  if (copy && count) PLM_CUDA(cudaMemcpyAsync(*dp, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  return PLM_OK;
+}
+
+size_t a4_count(const plm_a4d& a) { return size_t(a.nstride) * size_t(std::max(a.ncomp, 1)); }
+
+}  // namespace
+
+extern "C" {
+
+int plm_react_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, plm_a4d rYsrc, plm_a4d T,
+                  plm_a4d rEner, plm_a4d rEner_src, plm_a4d FC, plm_a4i mask, double* dt_react, double* time,
+                  void* cuda_stream)
+{
+  if (!r || !lo || !hi || !dt_react || !time) return fail(PLM_ERR_ARG, "null argument");
+  if (!r->inited) return fail(PLM_ERR_ARG, "plm_reactor_init has not been called");
+  if (!rY.p || !rYsrc.p || !T.p || !rEner.p || !rEner_src.p || !FC.p) return fail(PLM_ERR_ARG, "null array");
+  const int ns = r->tables->ns;
+  if (rY.ncomp < ns || rYsrc.ncomp < ns) return fail(PLM_ERR_ARG, "rY/rYsrc need NUM_SPECIES components");
+  for (int d = 0; d < 3; ++d) {
+    if (hi[d] < lo[d]) {  // empty box: nothing to do (amrex::ParallelFor over an empty box)
+      std::memset(&r->last, 0, sizeof(r->last));
+      return PLM_OK;
+    }
+    const plm_a4d* arrs[6] = {&rY, &rYsrc, &T, &rEner, &rEner_src, &FC};
+    for (auto* a : arrs)
+      if (lo[d] < a->lo[d] || hi[d] > a->hi[d]) return fail(PLM_ERR_ARG, "box is not contained in an array's bounds");
+    if (mask.p && (lo[d] < mask.lo[d] || hi[d] > mask.hi[d])) return fail(PLM_ERR_ARG, "box is not contained in mask bounds");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  plm::BoxArgs a{};
+  for (int d = 0; d < 3; ++d) {
+    a.lo[d] = lo[d];
+    a.hi[d] = hi[d];
+  }
+  a.ncells = int64_t(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+  a.flat = 0;
+  a.dt = *dt_react;
+  a.time = *time;
+  const bool dev = is_device_ptr(rY.p);
+  a.rY = rY; a.rYsrc = rYsrc; a.T = T; a.rE = rEner; a.rEsrc = rEner_src; a.FC = FC; a.mask = mask;
+  if (!dev) {
+    int rc;
+    if ((rc = stage_in(r->stage[0], rY.p, a4_count(rY), &a.rY.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[1], rYsrc.p, a4_count(rYsrc), &a.rYsrc.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[2], T.p, a4_count(T), &a.T.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[3], rEner.p, a4_count(rEner), &a.rE.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[4], rEner_src.p, a4_count(rEner_src), &a.rEsrc.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[5], FC.p, a4_count(FC), &a.FC.p, st, true))) return rc;
+    if (mask.p) {
+      const size_t cnt = size_t(mask.nstride) * size_t(std::max(mask.ncomp, 1));
+      if ((rc = stage_in(r->stage[6], mask.p, cnt, &a.mask.p, st, true))) return rc;
+    }
+  }
+  int rc = run_react(r, a, st);
+  if (rc != PLM_OK) return rc;
+  if (!dev) {
+    PLM_CUDA(cudaMemcpyAsync(rY.p, a.rY.p, a4_count(rY) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(T.p, a.T.p, a4_count(T) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(rEner.p, a.rE.p, a4_count(rEner) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(FC.p, a.FC.p, a4_count(FC) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaStreamSynchronize(st));
+  }
+  return PLM_OK;
+}
+
+int plm_react_flat(plm_reactor* r, double* rY, double* rYsrc, double* rX, double* rX_src, double* dt_react,
+                   double* time, int ncells, void* cuda_stream)
+{
+  if (!r || !rY || !rYsrc || !rX || !rX_src || !dt_react || !time) return fail(PLM_ERR_ARG, "null argument");
+  if (!r->inited) return fail(PLM_ERR_ARG, "plm_reactor_init has not been called");
+  if (ncells < 0) return fail(PLM_ERR_ARG, "negative ncells");
+  if (ncells == 0) {
+    std::memset(&r->last, 0, sizeof(r->last));
+    return PLM_OK;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int ns = r->tables->ns, n = ns + 1;
+  plm::BoxArgs a{};
+  a.ncells = ncells;
+  a.flat = 1;
+  a.hi[0] = ncells - 1;
+  a.dt = *dt_react;
+  a.time = *time;
+  const bool dev = is_device_ptr(rY);
+  double *dY = rY, *dS = rYsrc, *dX = rX, *dXs = rX_src, *dFC = nullptr;
+  int rc;
+  if (!dev) {
+    if ((rc = stage_in(r->stage[0], rY, size_t(ncells) * n, &dY, st, true))) return rc;
+    if ((rc = stage_in(r->stage[1], rYsrc, size_t(ncells) * ns, &dS, st, true))) return rc;
+    if ((rc = stage_in(r->stage[3], rX, size_t(ncells), &dX, st, true))) return rc;
+    if ((rc = stage_in(r->stage[4], rX_src, size_t(ncells), &dXs, st, true))) return rc;
+  }
+  if ((rc = stage_in(r->stage[5], static_cast<double*>(nullptr), size_t(ncells), &dFC, st, false))) return rc;
+  a.rY.p = dY; a.rYsrc.p = dS; a.T.p = dY; a.rE.p = dX; a.rEsrc.p = dXs; a.FC.p = dFC; a.mask.p = nullptr;
+  rc = run_react(r, a, st);
+  if (rc != PLM_OK) return rc;
+  if (!dev) {
+    PLM_CUDA(cudaMemcpyAsync(rY, dY, size_t(ncells) * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(rX, dX, size_t(ncells) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaStreamSynchronize(st));
+  }
+  return PLM_OK;
+}
+
+int plm_reactor_stats(plm_reactor* r, plm_stats* out)
+{
+  if (!r || !out) return fail(PLM_ERR_ARG, "null argument");
+  *out = r->last;
+  return PLM_OK;
+}
+
+int plm_reactor_cell_status(plm_reactor* r, int* dst, int64_t ncells)
+{
+  if (!r || !dst) return fail(PLM_ERR_ARG, "null argument");
+  if (ncells > r->last_ncells) return fail(PLM_ERR_ARG, "more cells requested than the last call processed");
+  PLM_CUDA(cudaMemcpy(dst, r->status.p, size_t(ncells) * sizeof(int),
+                      is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+  return PLM_OK;
+}
+
+void plm_reactor_close(plm_reactor* r)
+{
+  if (!r) return;
+  plm::free_dev_mech(&r->mech);
+  r->ctrl.release();
+  r->status.release();
+  r->jglobal.release();
+  for (auto& b : r->stage) b.release();
+  for (auto& b : r->scratch) b.release();
+  if (r->ev0) cudaEventDestroy(r->ev0);
+  if (r->ev1) cudaEventDestroy(r->ev1);
+  delete r;
+}
+
+int plm_eval_rhs(plm_reactor* r, int ncells, double t, const double* y, const double* rhoe_init,
+                 const double* rhoesrc_ext, const double* rYsrc, double* ydot, void* cuda_stream)
+{
+  if (!r || !y || !rhoe_init || !rhoesrc_ext || !rYsrc || !ydot) return fail(PLM_ERR_ARG, "null argument");
+  if (ncells <= 0) return PLM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int ns = r->tables->ns, n = ns + 1;
+  const bool dev = is_device_ptr(y);
+  double *dy = const_cast<double*>(y), *de = const_cast<double*>(rhoe_init), *des = const_cast<double*>(rhoesrc_ext),
+         *ds = const_cast<double*>(rYsrc), *dout = ydot;
+  int rc;
+  if (!dev) {
+    if ((rc = stage_in(r->scratch[0], y, size_t(ncells) * n, &dy, st, true))) return rc;
+    if ((rc = stage_in(r->scratch[1], rhoe_init, size_t(ncells), &de, st, true))) return rc;
+    if ((rc = stage_in(r->scratch[2], rhoesrc_ext, size_t(ncells), &des, st, true))) return rc;
+    if ((rc = stage_in(r->scratch[3], rYsrc, size_t(ncells) * ns, &ds, st, true))) return rc;
+    if ((rc = stage_in(r->scratch[4], static_cast<double*>(nullptr), size_t(ncells) * n, &dout, st, false))) return rc;
+  }
+  PLM_CUDA(plm::launch_rhs(r->mech.h, ncells, t, dy, de, des, ds, dout, st));
+  if (!dev) PLM_CUDA(cudaMemcpyAsync(ydot, dout, size_t(ncells) * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLM_CUDA(cudaStreamSynchronize(st));
+  return PLM_OK;
+}
+
+int plm_eval_jac(plm_reactor* r, int ncells, const double* y, double* J, void* cuda_stream)
+{
+  if (!r || !y || !J) return fail(PLM_ERR_ARG, "null argument");
+  if (ncells <= 0) return PLM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int n = r->tables->ns + 1;
+  const bool dev = is_device_ptr(y);
+  double *dy = const_cast<double*>(y), *dJ = J;
+  int rc;
+  if (!dev) {
+    if ((rc = stage_in(r->scratch[0], y, size_t(ncells) * n, &dy, st, true))) return rc;
+    if ((rc = stage_in(r->scratch[5], static_cast<double*>(nullptr), size_t(ncells) * n * n, &dJ, st, false))) return rc;
+  }
+  PLM_CUDA(plm::launch_jac(r->mech.h, ncells, dy, dJ, st));
+  if (!dev) PLM_CUDA(cudaMemcpyAsync(J, dJ, size_t(ncells) * n * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PLM_CUDA(cudaStreamSynchronize(st));
+  return PLM_OK;
+}
+
+int plm_box_costs(const double* FC, const int64_t* box_offsets, int nboxes, int64_t* costs, void* cuda_stream)
+{
+  if (!FC || !box_offsets || !costs || nboxes < 0) return fail(PLM_ERR_ARG, "bad argument");
+  if (nboxes == 0) return PLM_OK;
+  if (!is_device_ptr(FC) || !is_device_ptr(box_offsets) || !is_device_ptr(costs))
+    return fail(PLM_ERR_ARG, "plm_box_costs takes device pointers");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  PLM_CUDA(plm::launch_box_costs(FC, box_offsets, nboxes, reinterpret_cast<long long*>(costs), st));
+  return PLM_OK;
+}
+
+}  // extern "C"

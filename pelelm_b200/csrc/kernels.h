@@ -1,0 +1,51 @@
+// Host <-> kernel interface shared by kernels.cu and capi.cpp.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/plm_chem.h"
+#include "dev_tables.h"
+
+namespace plm {
+
+constexpr int kReactThreads = 128;   // 4 warps = 4 cells in flight per CTA
+constexpr int kCellsPerGrab = 4;     // consecutive cells a warp takes from the queue at once
+constexpr int kIntegCvode = 0, kIntegRK64 = 1;
+constexpr int kMaxN = 64;
+
+struct ReactOpts {
+  double rtol, atol;
+  int qmax, maxcor, ajac, use_typ, clean_init_massfrac;
+  int rk64_guess, rk64_min, rk64_max;
+  double typ_vals[kMaxN];
+};
+
+struct BoxArgs {
+  int lo[3], hi[3];
+  int64_t ncells;
+  int flat;    // 1: AoS flat API (rY [c][n] incl. T, rYsrc [c][ns], rE/rEsrc/FC [c])
+  int ld;
+  plm_a4d rY, rYsrc, T, rE, rEsrc, FC;
+  plm_a4i mask;
+  double dt, time;
+};
+
+struct LaunchCfg {
+  int blocks, threads;
+  size_t smem_bytes;
+};
+
+int ld_for(const DevMech& m);
+size_t react_smem_bytes(const DevMech& m, int qmax, bool j_in_smem, int warps_per_block);
+int react_occupancy(const DevMech& m, int integ, int threads, size_t smem);
+cudaError_t launch_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a, const LaunchCfg& cfg, int integ,
+                         unsigned long long* counter, unsigned long long* gstats, int* status, double* jglobal,
+                         cudaStream_t stream);
+cudaError_t launch_rhs(const DevMech& m, int ncells, double t, const double* y, const double* rhoe,
+                       const double* rhoesrc, const double* rYsrc, double* ydot, cudaStream_t stream);
+cudaError_t launch_jac(const DevMech& m, int ncells, const double* y, double* J, cudaStream_t stream);
+cudaError_t launch_box_costs(const double* FC, const int64_t* off, int nboxes, long long* costs, cudaStream_t stream);
+
+}  // namespace plm
