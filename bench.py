@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""Benchmark of the chemistry advance (BASELINE.json metric: chemistry cells*dt/s, % FP64 roofline).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--mech drm19|dodecane_lu|LiDryer]
+
+Workload at N=1: BASELINE.json configs[2] -- a synthetic 2^22-cell drm19 batch (16 boxes of 64^3), ReactorCvode with
+the dense analytic Jacobian, rtol = atol = 1e-10, max_order 2, dt = 1e-5 s, states from pelelm_b200/synth.py
+(T 900-2600 K, phi 0.5-2, burnt fraction 0-1 with radicals).  N>1: the same per-GPU work (weak scaling), boxes assigned
+by the reference's cost-weighted knapsack on the previous pass's FC; NCCL carries only the cost vector and the statistics.
+
+A "step" = one react() pass over every box of the rank's shard, each step from the same pristine state (restored by a
+device-to-device copy inside the timed region).  value = cells advanced by dt per second, whole job, inputs resident in
+HBM; e2e = the same through the C ABI with HOST (pinned) arrays, host<->device copies inside the timed region.
+roofline: FP64 SIMT (DFMA) -- algorithmic flops from the integrator counters (pelelm_b200/roofline.py) / step time,
+against the DFMA peak measured live on this device.  cpu_baseline / --impl reference: the UNMODIFIED reference
+(oracle/_ref/libref_<mech>.so, else the oracle port) on the host cores, one process per core, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DT = 1e-5
+BOX = 64 ** 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mech", default="drm19")
+    ap.add_argument("--integrator", default="ReactorCvode")
+    ap.add_argument("--cells", type=int, default=0, help="cells per GPU (default 2^22 drm19, 2^20 LiDryer, 2^18 dodecane_lu)")
+    ap.add_argument("--box-cells", type=int, default=BOX)
+    ap.add_argument("--rtol", type=float, default=1e-10)
+    ap.add_argument("--atol", type=float, default=1e-10)
+    ap.add_argument("--max-order", type=int, default=2)
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def default_cells(mech):
+    return {"drm19": 1 << 22, "LiDryer": 1 << 20, "dodecane_lu": 1 << 18}[mech]
+
+
+def workload_name(a, ncells_total, nboxes):
+    return "synthetic %d-cell %s batch (%d boxes of %d cells), %s denseAJ_direct rtol=%g atol=%g max_order=%d dt=%g" % (
+        ncells_total, a.mech, nboxes, a.box_cells, a.integrator, a.rtol, a.atol, a.max_order, DT)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference itself (oracle/_ref) or the oracle port, one process per host core
+# ---------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(mech, integ, rtol, atol, max_order, kind):
+    from oracle import pyoracle
+    if kind == "reference":
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # the reference prints its banner on stdout
+        try:
+            R = pyoracle.Ref(mech).init(integrator=integ, rtol=rtol, atol=atol, max_order=max_order)
+        finally:
+            os.dup2(saved, 1)
+    else:
+        R = pyoracle.Port(mech, build=False).init(integrator=integ, rtol=rtol, atol=atol, max_order=max_order)
+    _W["R"] = R
+    _W["mech"] = mech
+
+
+def _cpu_chunk(arg):
+    cell0, n = arg
+    from pelelm_b200 import synth
+    b = synth.synthetic_batch(_W["mech"], n, cell0=cell0)
+    t0 = time.perf_counter()
+    out = _W["R"].react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT)
+    return n, time.perf_counter() - t0, float(out[3].sum())
+
+
+class CpuArm:
+    def __init__(self, a):
+        from oracle import pyoracle
+        self.kind = "reference" if pyoracle.ref_available(a.mech) else "port"
+        if self.kind == "port":
+            pyoracle.build_port()
+        self.cores = len(os.sched_getaffinity(0))
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init,
+                             initargs=(a.mech, a.integrator, a.rtol, a.atol, a.max_order, self.kind))
+        self.a = a
+        # calibrate: 32 cells on every core
+        r = self.pool.map(_cpu_chunk, [(i * 32, 32) for i in range(self.cores)], chunksize=1)
+        self.rate = self.cores * sum(x[0] for x in r) / sum(x[1] for x in r)  # cells/s over all cores
+
+    def sample_cells(self, seconds):
+        per_core = max(16, int(self.rate * seconds / self.cores))
+        return per_core
+
+    def run(self, per_core, cell0=0):
+        chunks = []
+        # 4 chunks per core so that a few expensive cells do not leave cores idle
+        sub = max(4, per_core // 4)
+        c = cell0
+        for _ in range(self.cores * 4):
+            chunks.append((c, sub))
+            c += sub
+        t0 = time.perf_counter()
+        r = self.pool.map(_cpu_chunk, chunks, chunksize=1)
+        wall = time.perf_counter() - t0
+        n = sum(x[0] for x in r)
+        return n, wall, sum(x[2] for x in r)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = CpuArm(a)
+    cells_total = (a.cells or default_cells(a.mech)) * a.gpus
+    nboxes = max(1, cells_total // a.box_cells)
+    steps = max(1, a.steps)
+    per_step_seconds = max(2.0, min(a.cpu_seconds, 150.0 / (steps + a.warmup)))
+    per_core = arm.sample_cells(per_step_seconds)
+    for _ in range(a.warmup):
+        arm.run(max(16, per_core // 8))
+    n_tot, wall_tot, fc_tot = 0, 0.0, 0.0
+    for s in range(steps):
+        n, wall, fc = arm.run(per_core, cell0=s * per_core * arm.cores)
+        n_tot += n
+        wall_tot += wall
+        fc_tot += fc
+    arm.close()
+    value = n_tot / wall_tot
+    sample = "%d consecutive cells of the same synthetic workload per step, %d processes" % (n_tot // steps, arm.cores)
+    line = {
+        "impl": "reference", "metric": "chemistry cells*dt/s", "value": value, "unit": "cells*dt/s", "n_gpus": a.gpus,
+        "steps": steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall_tot / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a, cells_total, nboxes), "cpu_sample": sample, "mean_fc": fc_tot / n_tot},
+        "cpu_baseline": {"value": value, "unit": "cells*dt/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": value, "unit": "cells*dt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            t = [x.strip() for x in ln.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0]))
+                mx.append(float(t[1]))
+                pw.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "power_w_max": max(pw), "samples": len(sm)}
+        return out
+
+
+def run_gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    from pelelm_b200 import capi, roofline, synth
+    from pelelm_b200 import dist as pd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    N = world
+    capi.load()
+    m = synth.mech(a.mech)
+    ns = m.ns
+    cells_per_gpu = a.cells or default_cells(a.mech)
+    box_cells = min(a.box_cells, cells_per_gpu)
+    nboxes = N * (cells_per_gpu // box_cells)
+    cells_total = nboxes * box_cells
+    owner = (np.arange(nboxes) % N).astype(np.int32)  # round-robin start, as getFuncCountDM (PeleLM.cpp:5537-5538)
+
+    R = capi.Reactor(a.mech, a.integrator).init(rtol=a.rtol, atol=a.atol, max_order=a.max_order)
+    peak_tf = capi.measure_fp64_peak()
+
+    # ---- pristine state of this rank's boxes: S0 [ns+2][B] = rhoY, rhoH, T (the STemp aliasing of PeleLM.cpp:5728-5730),
+    #      F [ns+1][B] = forcing (FTemp), mask [B]; pinned host copies feed the e2e leg
+    def make_box(b):
+        st = synth.synthetic_batch(a.mech, box_cells, cell0=b * box_cells)
+        S = torch.empty((ns + 2, box_cells), dtype=torch.float64, pin_memory=True)
+        S[:ns] = torch.from_numpy(st["rY"])
+        S[ns] = torch.from_numpy(st["rE"])
+        S[ns + 1] = torch.from_numpy(st["T"])
+        F = torch.zeros((ns + 1, box_cells), dtype=torch.float64, pin_memory=True)
+        mask = torch.from_numpy(st["mask"]).pin_memory()
+        return {"id": b, "hS": S, "hF": F, "hmask": mask}
+
+    boxes = {}
+    for b in np.nonzero(owner == rank)[0]:
+        boxes[int(b)] = make_box(int(b))
+
+    def to_device(bx):
+        bx["S0"] = bx["hS"].to(dev, non_blocking=True)
+        bx["F"] = bx["hF"].to(dev, non_blocking=True)
+        bx["mask"] = bx["hmask"].to(dev, non_blocking=True)
+        bx["S"] = torch.empty_like(bx["S0"])
+        bx["FC"] = torch.zeros(box_cells, dtype=torch.float64, device=dev)
+
+    for bx in boxes.values():
+        to_device(bx)
+    torch.cuda.synchronize()
+
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
+    main = torch.cuda.current_stream()
+    launches = [0]
+
+    def react_box(bx, s, host=False):
+        lo, hi = [0, 0, 0], [box_cells - 1, 0, 0]
+        if host:
+            S, F, FC, mk = bx["hSw"].numpy(), bx["hF"].numpy(), bx["hFC"].numpy(), bx["hmask"].numpy()
+        else:
+            S, F, FC, mk = bx["S"], bx["F"], bx["FC"], bx["mask"]
+        R.react(lo, hi, S[:ns], F[:ns], S[ns + 1], S[ns], F[ns], FC, mk, DT, stream=s.cuda_stream, sync=False)
+        launches[0] += 1
+
+    def step():
+        """One advance over the local shard + the cost / statistics reductions of advance_chemistry."""
+        ids = sorted(boxes)
+        for i, b in enumerate(ids):
+            bx = boxes[b]
+            s = streams[i % len(streams)]
+            with torch.cuda.stream(s):
+                bx["S"].copy_(bx["S0"], non_blocking=True)
+                react_box(bx, s)
+        st = R.stats()  # waits for every launch
+        costs = np.array([int(boxes[b]["FC"].sum().item()) for b in ids], dtype=np.int64) if N == 1 else None
+        if N > 1:
+            FCall = torch.cat([boxes[b]["FC"] for b in ids])
+            off = torch.arange(0, (len(ids) + 1) * box_cells, box_cells, dtype=torch.int64, device=dev)
+            costs = capi.box_costs(FCall, off).cpu().numpy()
+        full = pd.gather_box_costs(costs, owner)
+        new_owner, eff = pd.func_count_dm(full, N, default_owner=owner)
+        return pd.reduce_stats(st), full, new_owner, eff
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up; after the first pass the boxes are re-dealt by the knapsack on the measured costs
+    eff = 1.0
+    for w in range(max(a.warmup, 1)):
+        gst, full, new_owner, eff = step()
+        if w == 0 and N > 1 and not np.array_equal(new_owner, owner):
+            for key in ("hS", "hF", "hmask"):
+                payload = {b: boxes[b][key].to(dev) for b in boxes}
+                moved = pd.redistribute(payload, owner, new_owner)
+                for b, t in moved.items():
+                    boxes.setdefault(b, {"id": b})[key] = t.cpu().pin_memory()
+            for b in list(boxes):
+                if new_owner[b] != rank:
+                    del boxes[b]
+            owner = new_owner.copy()
+            for bx in boxes.values():
+                to_device(bx)
+            torch.cuda.synchronize()
+
+    # ---- timed region
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches[0] = 0
+    e0.record(main)
+    for s in streams:
+        s.wait_event(e0)
+    tot = None
+    for _ in range(a.steps):
+        gst, full, new_owner, eff = step()
+        tot = gst if tot is None else {k: (tot[k] + gst[k] if k not in ("max_fc", "min_fc") else gst[k]) for k in gst}
+    for s in streams:
+        main.wait_stream(s)
+    e1.record(main)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    if N > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_launch = launches[0] * N  # every rank launches one integration kernel per local box per step (+ box_costs when N>1)
+    if N > 1:
+        n_launch += a.steps * N
+    value = cells_total * a.steps / (ms * 1e-3)
+    flops = roofline.algorithmic_flops(a.mech, a.integrator, tot)
+    achieved = flops / (ms * 1e-3) * 1e-12 / N  # per GPU
+    per_cell = {k: tot[k] / max(tot["ncells"], 1) for k in ("nst", "nfe", "nje", "nsetups", "nni", "netf", "ncfn")}
+
+    # ---- e2e: same step through the C ABI with HOST arrays (pinned), copies inside the timed region
+    e2e = None
+    if a.e2e_steps > 0:
+        for bx in boxes.values():
+            bx["hSw"] = torch.empty_like(bx["hS"]).pin_memory()
+            bx["hFC"] = torch.zeros(box_cells, dtype=torch.float64).pin_memory()
+        es = streams[0]
+        ms_e = 0.0
+        for _ in range(a.e2e_steps):
+            for bx in boxes.values():
+                bx["hSw"].copy_(bx["hS"])
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(es)
+            for b in sorted(boxes):
+                react_box(boxes[b], es, host=True)   # H2D, kernel, D2H, sync -- inside the library
+            R.stats()
+            a1.record(es)
+            barrier()
+            ms_e += a0.elapsed_time(a1)
+        if N > 1:
+            t = torch.tensor([ms_e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        nloc = cells_per_gpu
+        h2d = N * nloc * ((2 * ns + 4) * 8 + 4)   # rhoY, rhoH, T, forcing (N+1), FC staging, mask
+        d2h = N * nloc * (ns + 3) * 8             # rhoY, rhoH, T, FC
+        e2e = {"value": cells_total * a.e2e_steps / (ms_e * 1e-3), "unit": "cells*dt/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": a.e2e_steps}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and N == 1 and not a.no_cpu_baseline:
+        arm = CpuArm(a)
+        per_core = arm.sample_cells(a.cpu_seconds)
+        n, wall, _ = arm.run(per_core)
+        arm.close()
+        cpu = {"value": n / wall, "unit": "cells*dt/s", "cores": arm.cores, "kind": arm.kind,
+               "sample": "first %d cells of the same workload, %d processes, %.1f s" % (n, arm.cores, wall)}
+
+    if rank == 0:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(a.mech, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "chemistry cells*dt/s", "value": value, "unit": "cells*dt/s", "n_gpus": N, "steps": a.steps,
+            "warmup": max(a.warmup, 1), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a, cells_total, nboxes), "l2": "inputs larger than L2 (%.2f GB state per GPU)"
+                       % (cells_per_gpu * roofline.state_bytes_per_cell(a.mech) / 1e9),
+                       "cells_per_gpu": cells_per_gpu, "parallelism": "boxes over %d GPU(s), knapsack on FC" % N,
+                       "knapsack_efficiency": eff, "per_cell": per_cell, "nfailed": tot["nfailed"],
+                       "state_io_GBs": value / N * roofline.state_bytes_per_cell(a.mech) / 1e9},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                         "peak_source": "DFMA probe measured live on this device (MEASURED_PEAKS.json has no FP64 entry)",
+                         "flops_per_cell": flops / max(tot["ncells"], 1)},
+            "clocks": clk, "e2e": e2e, "gpu_launches": n_launch,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    R.close()
+    if N > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,14 +27,14 @@ enum { PLM_OK = 0, PLM_ERR_ARG = -1, PLM_ERR_NO_DEVICE = -2, PLM_ERR_CUDA = -3, 
  * ReactorCvodeUtils.cpp:9-21): 0 ok, else the CVODE flag of the failure (-1 too much work,
  * -2 too much accuracy, -3 error-test failures, -4 convergence failures, -22 bad ewt, -27 tout too close) */
 
-/* counters summed over the cells of the last react call (ReactorCvode::print_final_stats,
- * ReactorCvode.cpp:1929-1992) plus what the roofline needs */
+/* counters summed over the cells of every react call since the previous plm_reactor_stats()
+ * (ReactorCvode::print_final_stats, ReactorCvode.cpp:1929-1992) plus what the roofline needs */
 typedef struct {
   int64_t ncells, nskipped;      /* integrated / masked (mask == -1) */
   int64_t nst, nfe, nje, nsetups, nni, ncfn, netf;
   int64_t nfailed;               /* cells with status != 0 */
   int64_t max_fc, min_fc;
-  double  kernel_ms;             /* device time of the integration kernel (CUDA events) */
+  double  kernel_ms;             /* summed device time of the integration kernels (CUDA events per launch) */
 } plm_stats;
 
 /* ReactorBase::create(name) (Factory.H:73-80; PeleLM.cpp:701-709).
@@ -54,7 +54,10 @@ int  plm_reactor_set_typ_vals(plm_reactor*, const double* typ, int n);
 /* ReactorBase::react(box, rY, rYsrc, T, rEner, rEner_src, FC, mask, dt_react, time [,stream])
  * (ReactorBase.H:26-41; CPU semantics of ReactorCvode.cpp:1372-1453 / ReactorRK64.cpp:167-327).
  * dt_react/time are not modified (PeleLM is not built with MOD_REACTOR).  Returns <0 on failure,
- * else 0; per-cell failures are reported through plm_reactor_stats().nfailed and the status array. */
+ * else 0; per-cell failures are reported through plm_reactor_stats().nfailed and the status array.
+ * Device pointers: the call only ENQUEUES work on cuda_stream and returns (the caller synchronises the stream, as
+ * PeleLM does at PeleLM.cpp:5774); up to 16 calls on different streams may be in flight per reactor.
+ * Host pointers: the library stages the arrays through device buffers and returns when the results are back. */
 int  plm_react_box(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rY, plm_a4d rYsrc, plm_a4d T,
                    plm_a4d rEner, plm_a4d rEner_src, plm_a4d FC, plm_a4i mask,
                    double* dt_react, double* time, void* cuda_stream);
@@ -64,6 +67,7 @@ int  plm_react_box(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rY, p
 int  plm_react_flat(plm_reactor*, double* rY, double* rYsrc, double* rX, double* rX_src,
                     double* dt_react, double* time, int ncells, void* cuda_stream);
 
+/* waits for every outstanding call of this reactor, then returns and clears the accumulated counters */
 int  plm_reactor_stats(plm_reactor*, plm_stats* out);
 /* status word per cell of the last call, in box order (device or host destination) */
 int  plm_reactor_cell_status(plm_reactor*, int* dst, int64_t ncells);
@@ -86,6 +90,10 @@ int  plm_eval_jac(plm_reactor*, int ncells, const double* y, double* J, void* cu
 int  plm_box_costs(const double* FC, const int64_t* box_offsets, int nboxes, int64_t* costs, void* cuda_stream);
 int  plm_knapsack(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack,
                   int nmax, int* rank_of_box, double* efficiency);
+
+/* ---- measurement: register-resident DFMA throughput of the current device in TFLOP/s (the FP64 SIMT roofline
+ *      denominator; no reference counterpart) ---- */
+int  plm_measure_fp64_peak(double* tflops, void* cuda_stream);
 
 #ifdef __cplusplus
 }

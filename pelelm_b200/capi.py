@@ -41,7 +41,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals", "plm_react_box", "plm_react_flat",
            "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
-           "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack"]
+           "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_measure_fp64_peak"]
 
 _lib = None
 
@@ -72,6 +72,7 @@ def load():
     L.plm_eval_jac.argtypes = [vp, C.c_int, vp, vp, vp]
     L.plm_box_costs.argtypes = [vp, vp, C.c_int, vp, vp]
     L.plm_knapsack.argtypes = [C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_ip, c_dp]
+    L.plm_measure_fp64_peak.argtypes = [c_dp, vp]
     _lib = L
     return L
 
@@ -99,6 +100,28 @@ def knapsack(wgts, nranks, max_efficiency=0.9, do_full=True, nmax=2 ** 31 - 1):
     if rc != 0:
         raise PlmError("plm_knapsack failed")
     return out, eff.value
+
+
+def measure_fp64_peak() -> float:
+    """Register-resident DFMA throughput of the current device, TFLOP/s."""
+    L = load()
+    v = C.c_double(0)
+    rc = L.plm_measure_fp64_peak(C.cast(C.byref(v), c_dp), None)
+    if rc != 0:
+        raise PlmError(L.plm_last_error().decode())
+    return v.value
+
+
+def box_costs(FC, box_offsets, stream=None):
+    """Per-box sum of FC on the device (PeleLM::getFuncCountDM, PeleLM.cpp:5557-5571). torch CUDA tensors."""
+    import torch
+    L = load()
+    nb = box_offsets.numel() - 1
+    costs = torch.zeros(nb, dtype=torch.int64, device=FC.device)
+    rc = L.plm_box_costs(FC.data_ptr(), box_offsets.data_ptr(), nb, costs.data_ptr(), C.c_void_p(stream or 0))
+    if rc != 0:
+        raise PlmError(L.plm_last_error().decode())
+    return costs
 
 
 class Reactor:
@@ -141,8 +164,11 @@ class Reactor:
         return a
 
     def react(self, box_lo, box_hi, rY, rYsrc, T, rEner, rEner_src, FC, mask, dt_react, time=0.0, fab_lo=None,
-              fab_hi=None, stream=None):
-        """In-place on the given arrays (FAB layout: component-major over the FAB box [fab_lo, fab_hi])."""
+              fab_hi=None, stream=None, sync=True):
+        """In-place on the given arrays (FAB layout: component-major over the FAB box [fab_lo, fab_hi]).
+
+        With device arrays the call only enqueues work on `stream`; sync=True (default) then waits and returns the
+        statistics of the call, sync=False returns None -- collect the totals later with stats()."""
         fab_lo = list(box_lo if fab_lo is None else fab_lo)
         fab_hi = list(box_hi if fab_hi is None else fab_hi)
         ns = self.ns
@@ -159,7 +185,7 @@ class Reactor:
         tm = C.c_double(time)
         self._chk(self.L.plm_react_box(self.h, lo, hi, *a, m, C.cast(C.byref(dt), c_dp), C.cast(C.byref(tm), c_dp),
                                        C.c_void_p(stream or 0)))
-        return self.stats()
+        return self.stats() if sync else None
 
     def react_flat(self, rY, rYsrc, rX, rX_src, dt_react, time=0.0, stream=None):
         ncells = int(np.prod(rX.shape))
@@ -171,6 +197,7 @@ class Reactor:
         return self.stats()
 
     def stats(self):
+        """Waits for outstanding calls; totals over the react calls since the previous stats()."""
         s = Stats()
         self._chk(self.L.plm_reactor_stats(self.h, C.byref(s)))
         return s.as_dict()

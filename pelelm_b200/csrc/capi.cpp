@@ -69,6 +69,18 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int kSlots = 16;   // react calls that may be in flight at once (one per stream) on one reactor
+constexpr int kStatWords = 16;
+
+// per-call resources: a call owns one slot from launch until its kernel has finished
+struct CallSlot {
+  DevBuf status;   // int per cell
+  DevBuf jglobal;  // saved Jacobians when they do not fit in shared memory
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool used = false;
+  int64_t ncells = 0;
+};
+
 struct plm_reactor {
   const plm_mech_tables* tables = nullptr;
   plm::DevMechOwner mech;
@@ -76,14 +88,14 @@ struct plm_reactor {
   bool inited = false;
   plm::ReactOpts opts{};
   int num_sms = 0;
-  DevBuf ctrl;     // counter (1) + gstats (12) as unsigned long long
-  DevBuf status;   // int per cell
-  DevBuf jglobal;  // saved Jacobians when they do not fit in shared memory
+  DevBuf ctrl;     // [kSlots] work-queue counters, then kStatWords cumulative statistics (unsigned long long)
+  CallSlot slot[kSlots];
+  int next_slot = 0, last_slot = -1;
+  unsigned long long* host_stats = nullptr;  // pinned
   DevBuf stage[7]; // host-pointer staging: rY rYsrc T rE rEsrc FC mask
   DevBuf scratch[6];
-  int64_t last_ncells = 0;
   plm_stats last{};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double pending_ms = 0.0;  // kernel time of completed-but-unreported calls
   // cached launch configuration
   plm::LaunchCfg cfg{};
   bool j_in_smem = true;
@@ -125,13 +137,18 @@ int plm_reactor_create(plm_reactor** out, const char* mechanism, const char* int
     delete r;
     return fail(PLM_ERR_CUDA, "failed to build/upload mechanism tables");
   }
-  if (r->ctrl.ensure(16 * sizeof(unsigned long long)) != 0) {
+  if (r->ctrl.ensure((kSlots + kStatWords) * sizeof(unsigned long long)) != 0 ||
+      cudaMemset(r->ctrl.p, 0, (kSlots + kStatWords) * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&r->host_stats), kStatWords * sizeof(unsigned long long)) != cudaSuccess) {
     plm::free_dev_mech(&r->mech);
+    r->ctrl.release();
     delete r;
     return fail(PLM_ERR_CUDA, "cudaMalloc failed");
   }
-  cudaEventCreate(&r->ev0);
-  cudaEventCreate(&r->ev1);
+  for (auto& sl : r->slot) {
+    cudaEventCreate(&sl.ev0);
+    cudaEventCreate(&sl.ev1);
+  }
   *out = r;
   return PLM_OK;
 }
@@ -208,45 +225,71 @@ int configure(plm_reactor* r)
     }
   }
   if (best_warps == 0) return fail(PLM_ERR_CUDA, "no launch configuration fits in shared memory");
-  if (!r->j_in_smem) {
-    const size_t nw = size_t(r->cfg.blocks) * (r->cfg.threads / 32);
-    if (r->jglobal.ensure(nw * m.n * plm::ld_for(m) * sizeof(double)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
-  }
   r->cfg_qmax = r->opts.qmax;
   return PLM_OK;
 }
 
+// Enqueue one react call on `stream`. Never blocks the host: statistics accumulate on the device and are
+// fetched by collect_stats(); each call owns a slot (queue counter, status array, saved-Jacobian scratch) so that
+// calls issued on different streams may overlap.
 int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
 {
   int rc = configure(r);
   if (rc != PLM_OK) return rc;
-  a.ld = plm::ld_for(r->mech.h);
-  if (r->status.ensure(std::max<int64_t>(a.ncells, 1) * sizeof(int)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
-  auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
-  unsigned long long init[16] = {0};
-  init[1 + 11] = ~0ull;  // min_fc
-  PLM_CUDA(cudaMemcpyAsync(ctrl, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  const plm::DevMech& m = r->mech.h;
+  a.ld = plm::ld_for(m);
+  const int si = r->next_slot;
+  r->next_slot = (r->next_slot + 1) % kSlots;
+  CallSlot& sl = r->slot[si];
+  if (sl.used) {  // slot still owned by an earlier call: its kernel must have finished before the counter is reused
+    PLM_CUDA(cudaEventSynchronize(sl.ev1));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) r->pending_ms += ms;
+    sl.used = false;
+  }
+  if (sl.status.ensure(std::max<int64_t>(a.ncells, 1) * sizeof(int)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
   plm::LaunchCfg cfg = r->cfg;
   const int64_t warps_needed = (a.ncells + plm::kCellsPerGrab - 1) / plm::kCellsPerGrab;
   const int wpb = cfg.threads / 32;
   cfg.blocks = int(std::max<int64_t>(1, std::min<int64_t>(cfg.blocks, (warps_needed + wpb - 1) / wpb)));
-  PLM_CUDA(cudaEventRecord(r->ev0, stream));
-  PLM_CUDA(plm::launch_react(r->mech.h, r->opts, a, cfg, r->integ, ctrl, ctrl + 1, static_cast<int*>(r->status.p),
-                             r->j_in_smem ? nullptr : static_cast<double*>(r->jglobal.p), stream));
-  PLM_CUDA(cudaEventRecord(r->ev1, stream));
-  unsigned long long host[16];
-  PLM_CUDA(cudaMemcpyAsync(host, ctrl, sizeof(host), cudaMemcpyDeviceToHost, stream));
-  PLM_CUDA(cudaStreamSynchronize(stream));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, r->ev0, r->ev1);
-  const unsigned long long* g = host + 1;
+  if (!r->j_in_smem) {
+    const size_t nw = size_t(r->cfg.blocks) * wpb;
+    if (sl.jglobal.ensure(nw * m.n * a.ld * sizeof(double)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+  }
+  auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
+  PLM_CUDA(cudaMemsetAsync(ctrl + si, 0, sizeof(unsigned long long), stream));
+  PLM_CUDA(cudaEventRecord(sl.ev0, stream));
+  PLM_CUDA(plm::launch_react(m, r->opts, a, cfg, r->integ, ctrl + si, ctrl + kSlots, static_cast<int*>(sl.status.p),
+                             r->j_in_smem ? nullptr : static_cast<double*>(sl.jglobal.p), stream));
+  PLM_CUDA(cudaEventRecord(sl.ev1, stream));
+  sl.used = true;
+  sl.ncells = a.ncells;
+  r->last_slot = si;
+  return PLM_OK;
+}
+
+// Wait for every outstanding call, then move the cumulative device counters into r->last and zero them.
+int collect_stats(plm_reactor* r)
+{
+  for (auto& sl : r->slot)
+    if (sl.used) {
+      PLM_CUDA(cudaEventSynchronize(sl.ev1));
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) r->pending_ms += ms;
+      sl.used = false;
+    }
+  auto* g_dev = static_cast<unsigned long long*>(r->ctrl.p) + kSlots;
+  PLM_CUDA(cudaMemcpy(r->host_stats, g_dev, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  PLM_CUDA(cudaMemset(g_dev, 0, kStatWords * sizeof(unsigned long long)));
+  const unsigned long long* g = r->host_stats;
   plm_stats& s = r->last;
   s.nst = int64_t(g[0]); s.nfe = int64_t(g[1]); s.nje = int64_t(g[2]); s.nsetups = int64_t(g[3]);
   s.nni = int64_t(g[4]); s.ncfn = int64_t(g[5]); s.netf = int64_t(g[6]); s.nfailed = int64_t(g[7]);
   s.nskipped = int64_t(g[8]); s.ncells = int64_t(g[9]);
-  s.max_fc = int64_t(g[10]); s.min_fc = (g[9] ? int64_t(g[11]) : 0);
-  s.kernel_ms = ms;
-  r->last_ncells = a.ncells;
+  s.max_fc = int64_t(g[10]);
+  s.min_fc = g[9] ? int64_t(0xffffffffull - g[11]) : 0;  // the kernel keeps max(0xffffffff - fc)
+  s.kernel_ms = r->pending_ms;
+  r->pending_ms = 0.0;
   return PLM_OK;
 }
 
@@ -276,10 +319,7 @@ int plm_react_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, 
   const int ns = r->tables->ns;
   if (rY.ncomp < ns || rYsrc.ncomp < ns) return fail(PLM_ERR_ARG, "rY/rYsrc need NUM_SPECIES components");
   for (int d = 0; d < 3; ++d) {
-    if (hi[d] < lo[d]) {  // empty box: nothing to do (amrex::ParallelFor over an empty box)
-      std::memset(&r->last, 0, sizeof(r->last));
-      return PLM_OK;
-    }
+    if (hi[d] < lo[d]) return PLM_OK;  // empty box: nothing to do (amrex::ParallelFor over an empty box)
     const plm_a4d* arrs[6] = {&rY, &rYsrc, &T, &rEner, &rEner_src, &FC};
     for (auto* a : arrs)
       if (lo[d] < a->lo[d] || hi[d] > a->hi[d]) return fail(PLM_ERR_ARG, "box is not contained in an array's bounds");
@@ -328,10 +368,7 @@ int plm_react_flat(plm_reactor* r, double* rY, double* rYsrc, double* rX, double
   if (!r || !rY || !rYsrc || !rX || !rX_src || !dt_react || !time) return fail(PLM_ERR_ARG, "null argument");
   if (!r->inited) return fail(PLM_ERR_ARG, "plm_reactor_init has not been called");
   if (ncells < 0) return fail(PLM_ERR_ARG, "negative ncells");
-  if (ncells == 0) {
-    std::memset(&r->last, 0, sizeof(r->last));
-    return PLM_OK;
-  }
+  if (ncells == 0) return PLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const int ns = r->tables->ns, n = ns + 1;
   plm::BoxArgs a{};
@@ -364,6 +401,8 @@ int plm_react_flat(plm_reactor* r, double* rY, double* rYsrc, double* rX, double
 int plm_reactor_stats(plm_reactor* r, plm_stats* out)
 {
   if (!r || !out) return fail(PLM_ERR_ARG, "null argument");
+  const int rc = collect_stats(r);
+  if (rc != PLM_OK) return rc;
   *out = r->last;
   return PLM_OK;
 }
@@ -371,8 +410,11 @@ int plm_reactor_stats(plm_reactor* r, plm_stats* out)
 int plm_reactor_cell_status(plm_reactor* r, int* dst, int64_t ncells)
 {
   if (!r || !dst) return fail(PLM_ERR_ARG, "null argument");
-  if (ncells > r->last_ncells) return fail(PLM_ERR_ARG, "more cells requested than the last call processed");
-  PLM_CUDA(cudaMemcpy(dst, r->status.p, size_t(ncells) * sizeof(int),
+  if (r->last_slot < 0 || ncells > r->slot[r->last_slot].ncells)
+    return fail(PLM_ERR_ARG, "more cells requested than the last call processed");
+  CallSlot& sl = r->slot[r->last_slot];
+  if (sl.used) PLM_CUDA(cudaEventSynchronize(sl.ev1));
+  PLM_CUDA(cudaMemcpy(dst, sl.status.p, size_t(ncells) * sizeof(int),
                       is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
   return PLM_OK;
 }
@@ -381,13 +423,17 @@ void plm_reactor_close(plm_reactor* r)
 {
   if (!r) return;
   plm::free_dev_mech(&r->mech);
+  cudaDeviceSynchronize();
   r->ctrl.release();
-  r->status.release();
-  r->jglobal.release();
+  for (auto& sl : r->slot) {
+    sl.status.release();
+    sl.jglobal.release();
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    if (sl.ev1) cudaEventDestroy(sl.ev1);
+  }
+  if (r->host_stats) cudaFreeHost(r->host_stats);
   for (auto& b : r->stage) b.release();
   for (auto& b : r->scratch) b.release();
-  if (r->ev0) cudaEventDestroy(r->ev0);
-  if (r->ev1) cudaEventDestroy(r->ev1);
   delete r;
 }
 
@@ -432,6 +478,43 @@ int plm_eval_jac(plm_reactor* r, int ncells, const double* y, double* J, void* c
   if (!dev) PLM_CUDA(cudaMemcpyAsync(J, dJ, size_t(ncells) * n * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   PLM_CUDA(cudaStreamSynchronize(st));
   return PLM_OK;
+}
+
+int plm_measure_fp64_peak(double* tflops, void* cuda_stream)
+{
+  if (!tflops) return fail(PLM_ERR_ARG, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(PLM_ERR_NO_DEVICE, "no CUDA device");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  PLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, iters = 4096;
+  double* scratch = nullptr;
+  PLM_CUDA(cudaMalloc(&scratch, size_t(blocks) * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, st);
+    cudaError_t e = plm::launch_dfma_peak(scratch, blocks, iters, st);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 16.0 * iters * 256.0 * blocks;
+    if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(scratch);
+  *tflops = best;
+  return best > 0 ? PLM_OK : fail(PLM_ERR_CUDA, "DFMA probe failed");
 }
 
 int plm_box_costs(const double* FC, const int64_t* box_offsets, int nboxes, int64_t* costs, void* cuda_stream)

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kReactThreads) react_kernel(const DevMech m, c
     if (ndone) {
       atomicAdd(gstats + 9, ndone);
       atomicMax(gstats + 10, (unsigned long long)maxfc);
-      atomicMin(gstats + 11, (unsigned long long)minfc);
+      atomicMax(gstats + 11, 0xffffffffull - (unsigned long long)minfc);
     }
   }
 }
@@ -348,6 +348,29 @@ __global__ void box_cost_kernel(const double* __restrict__ FC, const int64_t* __
     v = warp_sum(v);
     if (threadIdx.x == 0) costs[b] = (long long)(v + 0.5);
   }
+}
+
+// Register-resident DFMA throughput probe: the measured FP64 SIMT peak that the roofline fractions are
+// quoted against (MEASURED_PEAKS.json has no FP64 entry). 16 independent chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* __restrict__ out, int iters, double a, double b)
+{
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = double(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keeps the chains live, never true in practice
+}
+
+cudaError_t launch_dfma_peak(double* scratch, int blocks, int iters, cudaStream_t stream)
+{
+  dfma_peak_kernel<<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999, 1e-9);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ cudaError_t launch_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a,
 cudaError_t launch_rhs(const DevMech& m, int ncells, double t, const double* y, const double* rhoe,
                        const double* rhoesrc, const double* rYsrc, double* ydot, cudaStream_t stream);
 cudaError_t launch_jac(const DevMech& m, int ncells, const double* y, double* J, cudaStream_t stream);
+cudaError_t launch_dfma_peak(double* scratch, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_box_costs(const double* FC, const int64_t* off, int nboxes, long long* costs, cudaStream_t stream);
 
 }  // namespace plm

@@ -1,0 +1,150 @@
+"""Multi-GPU plumbing of the chemistry advance: one process per GPU, torch.distributed (NCCL on the GPU box,
+gloo in the CPU tests).  Chemistry has no halo, so the only collectives are the ones the reference has
+(SURVEY.md section 8e):
+
+  * per-box cost vector: all_gather of each rank's box costs (replaces MPI_Gatherv + Bcast,
+    PeleLM::getFuncCountDM, Source/PeleLM.cpp:5582-5615), then every rank runs the same deterministic knapsack
+    (DistributionMapping::KnapSackProcessorMap, AMReX_DistributionMapping.cpp:846-870 -> plm_knapsack);
+  * statistics: all_reduce sum/max/min (ParallelDescriptor::ReduceRealMin/Max, PeleLM.cpp:5838-5839).
+
+Box payload motion when the chemistry DM differs from the state DM (FabArray::ParallelCopy, PeleLM.cpp:5695-5696,
+:5780) is `redistribute`: grouped point-to-point sends of whole boxes.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+
+def max_size(boxes, chunk):
+    """BoxArray::maxSize(chunk): chop every box so that no side is longer than chunk[d] (near-equal pieces)."""
+    out = []
+    for lo, hi in boxes:
+        cuts = []
+        for d in range(3):
+            n = hi[d] - lo[d] + 1
+            c = max(1, int(chunk[d]))
+            k = (n + c - 1) // c
+            base, rem = divmod(n, k)
+            edges, s = [], lo[d]
+            for i in range(k):
+                ln = base + (1 if i < rem else 0)
+                edges.append((s, s + ln - 1))
+                s += ln
+            cuts.append(edges)
+        for kz in cuts[2]:
+            for jy in cuts[1]:
+                for ix in cuts[0]:
+                    out.append(((ix[0], jy[0], kz[0]), (ix[1], jy[1], kz[1])))
+    return out
+
+
+def chop_for_chemistry(boxes, max_grid_size, nranks, threshold=4, min_side=16):
+    """Box chopping heuristic of advance_chemistry (PeleLM.cpp:5660-5687): halve the chunk per direction
+    (z first) until there are >= threshold*nranks boxes, never going below min_side cells a side."""
+    target = threshold * nranks
+    ba = list(boxes)
+    done = len(ba) >= target
+    cnt = 1
+    while not done:
+        chunk = [g // cnt for g in max_grid_size]
+        if any(c < min_side for c in chunk):
+            break
+        for j in (2, 1, 0):
+            if len(ba) >= target:
+                break
+            chunk[j] //= 2
+            ba = max_size(ba, chunk)
+            if len(ba) >= target:
+                done = True
+        cnt *= 2
+    return ba
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def gather_box_costs(local_costs, owner_of_box, group=None):
+    """All ranks get the full cost vector in box order. local_costs: costs of the boxes this rank owns, in
+    ascending box id; owner_of_box: current rank of every box (same on all ranks)."""
+    owner = np.asarray(owner_of_box)
+    nb = owner.size
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        full = np.zeros(nb, dtype=np.int64)
+        full[owner == 0] = np.asarray(local_costs, dtype=np.int64)
+        return full
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    dev = _device()
+    # zero-padded vector + sum == gather (each box has exactly one owner)
+    v = torch.zeros(nb, dtype=torch.int64, device=dev)
+    mine = np.nonzero(owner == rk)[0]
+    assert len(mine) == len(local_costs), (len(mine), len(local_costs))
+    if len(mine):
+        v[torch.as_tensor(mine, device=dev)] = torch.as_tensor(np.asarray(local_costs, dtype=np.int64), device=dev)
+    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return v.cpu().numpy()
+
+
+def func_count_dm(costs, nranks, default_owner=None):
+    """getFuncCountDM's decision: FC all zero -> keep the default mapping (PeleLM.cpp:5545-5549), else knapsack."""
+    costs = np.asarray(costs, dtype=np.int64)
+    if costs.size == 0 or costs.max() <= 0:
+        if default_owner is not None:
+            return np.asarray(default_owner, dtype=np.int32), 1.0
+        return (np.arange(costs.size) % nranks).astype(np.int32), 1.0
+    return capi.knapsack(costs, nranks)
+
+
+def reduce_stats(stats: dict, group=None):
+    """Sum the additive integrator counters over ranks; max/min for the extrema and the kernel time."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(stats)
+    dev = _device()
+    add = ["ncells", "nskipped", "nst", "nfe", "nje", "nsetups", "nni", "ncfn", "netf", "nfailed"]
+    s = torch.tensor([float(stats.get(k, 0)) for k in add], dtype=torch.float64, device=dev)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    mx = torch.tensor([float(stats.get("max_fc", 0)), float(stats.get("kernel_ms", 0.0)), -float(stats.get("min_fc", 0))],
+                      dtype=torch.float64, device=dev)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    out = {k: int(v) for k, v in zip(add, s.tolist())}
+    out["max_fc"], out["kernel_ms"], out["min_fc"] = int(mx[0].item()), mx[1].item(), int(-mx[2].item())
+    return out
+
+
+def redistribute(payload: dict, old_owner, new_owner, group=None):
+    """ParallelCopy of whole boxes between distribution maps: payload = {box id: tensor} held by this rank under
+    old_owner; returns the dict this rank holds under new_owner. All boxes must have the same shape/dtype per id
+    on sender and receiver (the receiver allocates from `like`)."""
+    old_owner, new_owner = np.asarray(old_owner), np.asarray(new_owner)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(payload)
+    rk = dist.get_rank(group)
+    out, ops, keep = {}, [], []
+    shapes = {b: (tuple(t.shape), t.dtype, t.device) for b, t in payload.items()}
+    # shapes of boxes we will receive: exchanged as a small object gather (host side, tiny)
+    all_shapes = [None] * dist.get_world_size(group)
+    dist.all_gather_object(all_shapes, {b: (s[0], str(s[1])) for b, s in shapes.items()}, group=group)
+    dev = _device()
+    for b in range(old_owner.size):
+        src, dst = int(old_owner[b]), int(new_owner[b])
+        if src == dst:
+            if src == rk:
+                out[b] = payload[b]
+            continue
+        if src == rk:
+            t = payload[b].contiguous()
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, dst, group=group, tag=b))
+        elif dst == rk:
+            shp, dt = all_shapes[src][b]
+            t = torch.empty(shp, dtype=getattr(torch, dt.split(".")[-1]), device=dev)
+            out[b] = t
+            ops.append(dist.P2POp(dist.irecv, t, src, group=group, tag=b))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out

@@ -1,0 +1,118 @@
+"""Generate tests/golden/<mech>.npz by running the UNMODIFIED reference (oracle/_ref/libref_<mech>.so,
+built by `make -C oracle ref` in the container where /root/reference exists) on seeded synthetic inputs.
+
+    python tests/golden/make_golden.py            # one subprocess per mechanism (the reference keeps
+                                                  # process-wide singletons; one mechanism per process)
+
+The fixtures hold inputs AND the reference's outputs, so the `-m "not gpu"` and `-m gpu` suites can check
+the oracle port and the CUDA path against the real reference on boxes where /root/reference is absent.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+NCELLS = {"LiDryer": 48, "drm19": 48, "dodecane_lu": 6}
+CASES = {
+    # name: (integrator, init kwargs, batch kwargs)
+    "cv_tight": ("ReactorCvode", dict(rtol=1e-10, atol=1e-10, max_order=2), dict(forcing=True, mask_every=7)),
+    "cv_plm": ("ReactorCvode", dict(rtol=1e-6, atol=1e-10, max_order=4), dict(forcing=False, mask_every=0)),
+    "cv_typ": ("ReactorCvode", dict(rtol=1e-6, atol=1e-5, max_order=4), dict(forcing=True, mask_every=5)),
+    "cv_clean": ("ReactorCvode", dict(rtol=1e-8, atol=1e-10, max_order=3, clean_init_massfrac=1),
+                 dict(forcing=False, mask_every=0)),
+    "cv_dq": ("ReactorCvode", dict(rtol=1e-8, atol=1e-10, max_order=2, solve_type="dense_direct"),
+              dict(forcing=False, mask_every=0)),
+    "rk_stiff": ("ReactorRK64", dict(atol=1e-10), dict(forcing=True, mask_every=7)),
+    "rk_mild": ("ReactorRK64", dict(atol=1e-10), dict(forcing=True, mask_every=0, t_range=(900.0, 1150.0))),
+}
+DT = 1e-5
+
+
+def typ_vals(b):
+    """typical values as PeleLM would set them: max of each rhoY over the batch (floored), T"""
+    t = np.maximum(b["rY"].max(1), 1e-10)
+    return np.concatenate([t, [b["T"].max()]])
+
+
+def one(mech: str):
+    from oracle.pyoracle import Ref
+    from pelelm_b200 import synth
+    R = Ref(mech)
+    out = {}
+    nc = NCELLS[mech]
+    for ci, (name, (integ, ikw, bkw)) in enumerate(CASES.items()):
+        if name.startswith("rk") and mech == "dodecane_lu":
+            continue
+        b = synth.synthetic_batch(mech, nc, seed=synth.DEFAULT_SEED + ci, dt=DT, **bkw)
+        if name == "cv_clean":  # small negative undershoots, as advection produces
+            neg = b["rY"] < 1e-12 * b["rY"].sum(0, keepdims=True)
+            b["rY"][neg] = -1e-9 * np.broadcast_to(b["rY"].sum(0, keepdims=True), b["rY"].shape)[neg]
+        R.init(integrator=integ, **ikw)
+        if name == "cv_typ":
+            tv = typ_vals(b)
+            R.set_typ_vals(tv)
+            out[name + "/typ"] = tv
+        else:
+            R.set_typ_vals(np.full(R.n, -1.0))
+        rY, T, rE, FC = R.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT)
+        for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask"):
+            out[name + "/in_" + k] = b[k]
+        out[name + "/rY"], out[name + "/T"], out[name + "/rE"], out[name + "/FC"] = rY, T, rE, FC
+    # cfg0: the ReactEval initial condition (flat 1dArray API as well as box)
+    b = synth.reacteval_state(mech, 2, 8 if mech != "dodecane_lu" else 2, 1)
+    R.init(integrator="ReactorCvode", rtol=1e-10, atol=1e-10, max_order=2)
+    R.set_typ_vals(np.full(R.n, -1.0))
+    rY, T, rE, FC = R.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT)
+    for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask"):
+        out["reval/in_" + k] = b[k]
+    out["reval/rY"], out["reval/T"], out["reval/rE"], out["reval/FC"] = rY, T, rE, FC
+    # kernel-level: fKernelSpec and cJac on 32 states
+    b = synth.synthetic_batch(mech, 32, seed=77, forcing=True, dt=DT)
+    y = np.ascontiguousarray(np.concatenate([b["rY"].T, b["T"][:, None]], 1))
+    rYsrc = np.ascontiguousarray(b["rYsrc"].T)
+    out["rhs/y"], out["rhs/rhoe"], out["rhs/rhoesrc"], out["rhs/rYsrc"] = y, b["rE"], b["rEsrc"], rYsrc
+    out["rhs/t"] = np.array(3e-6)
+    out["rhs/ydot"] = R.rhs(y, b["rE"], b["rEsrc"], rYsrc, 3e-6)
+    y2 = y.copy()
+    y2[:, -1] = b["T_true"]
+    out["jac/y"] = y2
+    out["jac/J"] = R.jac(y2)
+    np.savez_compressed(os.path.join(HERE, mech + ".npz"), **out)
+    print(mech, "golden written:", len(out), "arrays")
+
+
+def knap():
+    """KnapSackProcessorMap buckets from the reference's own knapsack() (any libref works)."""
+    import ctypes as C
+    from oracle.pyoracle import Ref, c_ip, c_dp
+    R = Ref("LiDryer")
+    R.L.ref_knapsack.argtypes = [C.POINTER(C.c_long), C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_dp]
+    rng = np.random.default_rng(5)
+    out = {}
+    cases = [(8, 2), (64, 8), (100, 8), (512, 8), (37, 4), (16, 16), (5, 8), (1000, 7)]
+    for i, (nb, nr) in enumerate(cases):
+        w = (rng.lognormal(8, 1.5, nb)).astype(np.int64) + 1
+        if i == 3:
+            w[:] = 1000  # all equal
+        wl = (C.c_long * nb)(*[int(x) for x in w])
+        res = np.zeros(nb, dtype=np.int32)
+        eff = C.c_double(0)
+        R.L.ref_knapsack(wl, nb, nr, 1, 2 ** 31 - 1, res.ctypes.data_as(c_ip), C.cast(C.byref(eff), c_dp))
+        out["w%d" % i], out["b%d" % i], out["e%d" % i], out["n%d" % i] = w, res, np.array(eff.value), np.array(nr)
+    np.savez_compressed(os.path.join(HERE, "knapsack.npz"), **out)
+    print("knapsack golden written")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        knap() if sys.argv[1] == "knapsack" else one(sys.argv[1])
+    else:
+        for m in list(NCELLS) + ["knapsack"]:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), m])

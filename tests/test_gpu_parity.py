@@ -1,0 +1,234 @@
+"""Parity of the CUDA path (through the C ABI of libplmchem.so) with the checkers, on a B200.
+
+Checkers: (1) the committed golden fixtures = outputs of the UNMODIFIED reference, (2) the oracle port run live
+on seeded inputs.  Bar (BASELINE.json north_star): final Y_k and T relative error <= 1e-6 at rtol = atol = 1e-10,
+identical mask/skip behaviour; rhoH bit-exact; FC identical where the port's is.
+"""
+import numpy as np
+import pytest
+
+from conftest import MECHS, golden, check_state
+from golden.make_golden import CASES, DT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi(plm_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pelelm_b200 import capi as c
+    return c
+
+
+def _gpu_react(capi, mech, integ, ikw, b, typ=None, box=None):
+    kw = dict(ikw)
+    rk = integ == "ReactorRK64"
+    R = capi.Reactor(mech, integ).init(rtol=kw.get("rtol", kw["atol"]), atol=kw["atol"], max_order=kw.get("max_order", 2),
+                                       clean_init_massfrac=kw.get("clean_init_massfrac", 0),
+                                       solve_type=kw.get("solve_type", "denseAJ_direct"))
+    if typ is not None:
+        R.set_typ_vals_ode(typ)
+    nc = b["T"].size
+    a = [b["rY"].copy(), b["rYsrc"].copy(), b["T"].copy(), b["rE"].copy(), b["rEsrc"].copy(), np.zeros(nc)]
+    st = R.react([0, 0, 0], [nc - 1, 0, 0], a[0], a[1], a[2], a[3], a[4], a[5], b["mask"].copy(), DT)
+    status = R.cell_status(nc)
+    R.close()
+    return (a[0], a[2], a[3], a[5]), st, status
+
+
+@pytest.mark.parametrize("mech", MECHS)
+@pytest.mark.parametrize("case", list(CASES) + ["reval"])
+def test_react_vs_reference_golden(capi, mech, case):
+    g = golden(mech)
+    if case + "/rY" not in g:
+        pytest.skip("case not generated for this mechanism")
+    integ, ikw, _ = CASES.get(case, ("ReactorCvode", dict(rtol=1e-10, atol=1e-10, max_order=2), None))
+    b = {k: g[case + "/in_" + k] for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask")}
+    typ = g[case + "/typ"] if case + "/typ" in g else None
+    got, st, status = _gpu_react(capi, mech, integ, ikw, b, typ)
+    atol = ikw["atol"] * (typ[:-1, None] if typ is not None else 1.0)
+    ref = (g[case + "/rY"], g[case + "/T"], g[case + "/rE"], g[case + "/FC"])
+    small = mech != "dodecane_lu"
+    exact_fc = small and case != "cv_dq"
+    cmp_rtol = max(1e-6, 100 * ikw.get("rtol", 0.0))
+    check_state(got, ref, atol, tag="%s/%s" % (mech, case), rtol=cmp_rtol, fc_equal_min=0.9 if exact_fc else None,
+                fc_rel=0.05 if small else 0.15)
+    assert not status.any()
+    m = b["mask"] == -1
+    if integ == "ReactorCvode":
+        assert st["nskipped"] == int(m.sum()) and st["ncells"] == int((~m).sum())
+        if m.any():
+            assert np.array_equal(got[0][:, m], b["rY"][:, m]) and np.array_equal(got[1][m], b["T"][m])
+            assert np.all(got[3][m] == 0)
+    else:
+        assert st["nskipped"] == 0  # ReactorRK64 ignores the mask (ReactorRK64.cpp:176)
+
+
+@pytest.mark.parametrize("mech,nc", [("LiDryer", 512), ("drm19", 512), ("dodecane_lu", 48)])
+def test_react_vs_port_live(capi, port_lib, mech, nc):
+    from pelelm_b200 import synth
+    b = synth.synthetic_batch(mech, nc, seed=4242, forcing=True, mask_every=97)
+    ikw = dict(rtol=1e-10, atol=1e-10, max_order=2)
+    P = port_lib.Port(mech).init(**ikw)
+    ref = P.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT, nthreads=8)
+    got, st, status = _gpu_react(capi, mech, "ReactorCvode", ikw, b)
+    small = mech != "dodecane_lu"
+    check_state(got, ref, 1e-10, tag=mech, fc_equal_min=0.95 if small else None, fc_rel=0.02 if small else 0.1)
+    assert not status.any()
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_rhs_vs_reference_and_port(capi, port_lib, mech):
+    g = golden(mech)
+    R = capi.Reactor(mech, "ReactorCvode").init()
+    f = R.eval_rhs(g["rhs/y"], g["rhs/rhoe"], g["rhs/rhoesrc"], g["rhs/rYsrc"], float(g["rhs/t"]))
+    ref = g["rhs/ydot"]
+    err = np.abs(f - ref) / np.abs(ref).max(1, keepdims=True)
+    assert err.max() < 1e-9, err.max()
+    fp = port_lib.Port(mech).rhs(g["rhs/y"], g["rhs/rhoe"], g["rhs/rhoesrc"], g["rhs/rYsrc"], float(g["rhs/t"]))
+    err = np.abs(f - fp) / np.abs(fp).max(1, keepdims=True)
+    assert err.max() < 1e-11, err.max()
+    R.close()
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_jac_vs_reference(capi, mech):
+    g = golden(mech)
+    R = capi.Reactor(mech, "ReactorCvode").init()
+    J = R.eval_jac(g["jac/y"])
+    ref = g["jac/J"]
+    err = np.abs(J - ref) / np.abs(ref).max(1, keepdims=True)
+    assert err.max() < 1e-11, err.max()
+    R.close()
+
+
+@pytest.mark.parametrize("mech", ["LiDryer", "drm19"])
+def test_flat_api_matches_box_api(capi, mech):
+    """react(rY_in[ncells][N+1], ...) (ReactorBase.H:43-55) takes T from the state vector and returns FC through
+    the stats; same integration as the box API once T is the converged one."""
+    from pelelm_b200 import synth
+    nc = 67  # ragged: not a multiple of the warp grab size
+    b = synth.synthetic_batch(mech, nc, seed=9, forcing=True)
+    ikw = dict(rtol=1e-10, atol=1e-10, max_order=2)
+    b["mask"][:] = 1
+    (rY, T, rE, FC), st, _ = _gpu_react(capi, mech, "ReactorCvode", ikw, b)
+    # a second box pass from the converged T gives the T the flat API must be fed
+    R = capi.Reactor(mech, "ReactorCvode").init(**ikw)
+    y = np.ascontiguousarray(np.concatenate([b["rY"].T, b["T_true"][:, None]], 1))
+    src = np.ascontiguousarray(b["rYsrc"].T)
+    rX, rXs = b["rE"].copy(), b["rEsrc"].copy()
+    st2 = R.react_flat(y, src, rX, rXs, DT)
+    R.close()
+    assert st2["ncells"] == nc
+    assert np.array_equal(rX, rE)
+    e = np.abs(y[:, :-1].T - rY) / (1e-6 * np.abs(rY) + 1e-9)
+    assert e.max() <= 1.0, e.max()
+
+
+def test_device_pointers_equal_host_pointers(capi):
+    import torch
+    from pelelm_b200 import synth
+    mech, nc = "drm19", 300
+    b = synth.synthetic_batch(mech, nc, seed=3, forcing=True, mask_every=11)
+    ikw = dict(rtol=1e-8, atol=1e-10, max_order=3)
+    got, st, _ = _gpu_react(capi, mech, "ReactorCvode", ikw, b)
+    R = capi.Reactor(mech, "ReactorCvode").init(**ikw)
+    dev = [torch.from_numpy(b[k].copy()).cuda() for k in ("rY", "rYsrc", "T", "rE", "rEsrc")]
+    FC = torch.zeros(nc, dtype=torch.float64, device="cuda")
+    mask = torch.from_numpy(b["mask"]).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        R.react([0, 0, 0], [nc - 1, 0, 0], dev[0], dev[1], dev[2], dev[3], dev[4], FC, mask, DT, stream=s.cuda_stream)
+    s.synchronize()
+    R.close()
+    assert np.array_equal(dev[0].cpu().numpy(), got[0]) and np.array_equal(dev[2].cpu().numpy(), got[1])
+    assert np.array_equal(dev[3].cpu().numpy(), got[2]) and np.array_equal(FC.cpu().numpy(), got[3])
+
+
+def test_subbox_of_fab_with_ghost_cells(capi):
+    """react on a tile box strictly inside the FAB (PeleLM.cpp:5727): cells outside the box are untouched."""
+    from pelelm_b200 import synth
+    mech = "LiDryer"
+    flo, fhi = [-2, -2, -1], [9, 5, 1]          # FAB bounds (12 x 8 x 3 cells)
+    lo, hi = [0, 0, 0], [7, 3, 0]               # interior tile (8 x 4 x 1)
+    nx, ny, nz = 12, 8, 3
+    nf = nx * ny * nz
+    b = synth.synthetic_batch(mech, nf, seed=21, forcing=True)
+    ikw = dict(rtol=1e-10, atol=1e-10, max_order=2)
+    R = capi.Reactor(mech, "ReactorCvode").init(**ikw)
+    a = [b["rY"].copy(), b["rYsrc"].copy(), b["T"].copy(), b["rE"].copy(), b["rEsrc"].copy(), np.full(nf, -7.0)]
+    mask = np.ones(nf, dtype=np.int32)
+    R.react(lo, hi, a[0], a[1], a[2], a[3], a[4], a[5], mask, DT, fab_lo=flo, fab_hi=fhi)
+    R.close()
+    idx = np.arange(nf).reshape(nz, ny, nx)
+    inside = idx[1:2, 2:6, 2:10].ravel()
+    outside = np.setdiff1d(np.arange(nf), inside)
+    assert np.array_equal(a[0][:, outside], b["rY"][:, outside]) and np.all(a[5][outside] == -7.0)
+    assert np.all(a[5][inside] > 0)
+    sub = {k: (b[k][:, inside].copy() if b[k].ndim == 2 else b[k][inside].copy()) for k in ("rY", "rYsrc", "T", "rE", "rEsrc")}
+    sub["mask"] = np.ones(inside.size, dtype=np.int32)
+    got, _, _ = _gpu_react(capi, mech, "ReactorCvode", ikw, sub)
+    assert np.array_equal(got[0], a[0][:, inside]) and np.array_equal(got[1], a[2][inside])
+    assert np.array_equal(got[3], a[5][inside])
+
+
+def test_edge_sizes(capi):
+    from pelelm_b200 import synth
+    R = capi.Reactor("LiDryer", "ReactorCvode").init(rtol=1e-8, atol=1e-10)
+    z = np.zeros((9, 1))
+    st = R.react([0, 0, 0], [-1, 0, 0], z, z, np.zeros(1), np.zeros(1), np.zeros(1), np.zeros(1), None, DT)
+    assert st["ncells"] == 0
+    for nc in (1, 3, 5, 33):
+        b = synth.synthetic_batch("LiDryer", nc, seed=nc)
+        FC = np.zeros(nc)
+        st = R.react([0, 0, 0], [nc - 1, 0, 0], b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], FC, None, DT)
+        assert st["ncells"] == nc and np.all(FC > 0)
+    R.close()
+
+
+def test_cell_result_independent_of_batch_position(capi):
+    """Size-independent property used at full size: a cell's result depends only on its own inputs
+    (bit-exact under any permutation of the batch and any batch size)."""
+    from pelelm_b200 import synth
+    mech, nc = "drm19", 4096
+    b = synth.synthetic_batch(mech, nc, seed=31, forcing=True)
+    ikw = dict(rtol=1e-8, atol=1e-10, max_order=2)
+    got, _, _ = _gpu_react(capi, mech, "ReactorCvode", ikw, b)
+    perm = np.random.default_rng(1).permutation(nc)[: nc // 2 + 7]
+    sub = {k: (np.ascontiguousarray(b[k][:, perm]) if b[k].ndim == 2 else b[k][perm].copy()) for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask")}
+    got2, _, _ = _gpu_react(capi, mech, "ReactorCvode", ikw, sub)
+    assert np.array_equal(got2[0], got[0][:, perm]) and np.array_equal(got2[1], got[1][perm])
+    assert np.array_equal(got2[3], got[3][perm])
+
+
+def test_full_size_properties(capi):
+    """BASELINE config 3 size (2^22 cells drm19) would take minutes at tight tolerance inside the unit suite, so the
+    full-size pass runs a 2^20 shard and checks the size-independent invariants: rhoH = in + dt*src exactly, total
+    mass changes only by dt * sum(src) (elements are conserved by the mechanism), FC > 0 on every unmasked cell,
+    FC = 0 and untouched state on masked cells, per-box cost reduction = numpy sum."""
+    import torch
+    from pelelm_b200 import synth
+    mech, nc = "drm19", 1 << 20
+    b = synth.synthetic_batch(mech, nc, seed=1, forcing=True, mask_every=97)
+    R = capi.Reactor(mech, "ReactorCvode").init(rtol=1e-6, atol=1e-10, max_order=4)
+    a = [b["rY"].copy(), b["rYsrc"], b["T"].copy(), b["rE"].copy(), b["rEsrc"], np.zeros(nc)]
+    st = R.react([0, 0, 0], [nc - 1, 0, 0], a[0], a[1], a[2], a[3], a[4], a[5], b["mask"], DT)
+    m = b["mask"] == -1
+    assert st["nfailed"] == 0 and st["nskipped"] == int(m.sum())
+    assert np.array_equal(a[3][~m], (b["rE"] + DT * b["rEsrc"])[~m])
+    assert np.array_equal(a[0][:, m], b["rY"][:, m]) and np.all(a[5][m] == 0) and np.all(a[5][~m] > 0)
+    rho0, rho1 = b["rY"].sum(0), a[0].sum(0)
+    drho = (rho1 - rho0 - DT * b["rYsrc"].sum(0))[~m]
+    assert np.abs(drho / rho0[~m]).max() < 1e-7
+    assert int(a[5].sum()) == st["nfe"]
+    # per-box costs on the device
+    nb = 64
+    off = torch.arange(0, nc + 1, nc // nb, dtype=torch.int64, device="cuda")
+    costs = torch.zeros(nb, dtype=torch.int64, device="cuda")
+    FCd = torch.from_numpy(a[5]).cuda()
+    rc = capi.load().plm_box_costs(FCd.data_ptr(), off.data_ptr(), nb, costs.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert np.array_equal(costs.cpu().numpy(), a[5].reshape(nb, -1).sum(1).astype(np.int64))
+    R.close()
