@@ -75,6 +75,8 @@ int  plm_reactor_cell_status(plm_reactor*, int* dst, int64_t ncells);
 void plm_reactor_close(plm_reactor*);
 
 int  plm_num_species(const plm_reactor*);
+/* species k in mechanism order (CKSYMS_STR, mechanism.cpp): lets a binding assert it was compiled for the same mechanism */
+const char* plm_species_name(const plm_reactor*, int k);
 const char* plm_last_error(void);
 
 /* ---- kernel-level entry points used by the parity tests (reference functions they mirror) ---- */

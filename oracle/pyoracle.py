@@ -37,10 +37,12 @@ def build_port():
 def build_ref():
     if os.path.isdir(os.environ.get("PLM_REFERENCE", "/root/reference")):
         subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+        if os.path.exists(os.path.join(os.path.dirname(HERE), "pelelm_b200", "libplmchem.so")):
+            subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref_b200"])
 
 
-def ref_available(mech: str) -> bool:
-    return os.path.exists(os.path.join(HERE, "_ref", "libref_%s.so" % mech))
+def ref_available(mech: str, b200: bool = False) -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_%s%s.so" % (mech, "_b200" if b200 else "")))
 
 
 class Opts(C.Structure):
@@ -61,8 +63,10 @@ class Stats(C.Structure):
 class Ref:
     """The reference itself. One mechanism per process-wide library; the reactor is (re)created by ``init``."""
 
-    def __init__(self, mech: str):
-        path = os.path.join(HERE, "_ref", "libref_%s.so" % mech)
+    def __init__(self, mech: str, b200: bool = False):
+        # b200=True: the same reference objects + the drop-in adaptor (pelelm_b200/adaptor), so that the reference's
+        # own factory can create "ReactorCvodeB200"/"ReactorRK64B200" (oracle/Makefile target ref_b200)
+        path = os.path.join(HERE, "_ref", "libref_%s%s.so" % (mech, "_b200" if b200 else ""))
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (run `make -C oracle ref` where /root/reference exists)")
         self.L = L = C.CDLL(path)

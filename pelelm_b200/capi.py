@@ -41,7 +41,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals", "plm_react_box", "plm_react_flat",
            "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
-           "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_measure_fp64_peak"]
+           "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_measure_fp64_peak", "plm_species_name"]
 
 _lib = None
 
@@ -68,6 +68,8 @@ def load():
     L.plm_reactor_close.restype = None
     L.plm_num_species.argtypes = [vp]
     L.plm_last_error.restype = C.c_char_p
+    L.plm_species_name.argtypes = [vp, C.c_int]
+    L.plm_species_name.restype = C.c_char_p
     L.plm_eval_rhs.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp, vp, vp]
     L.plm_eval_jac.argtypes = [vp, C.c_int, vp, vp, vp]
     L.plm_box_costs.argtypes = [vp, vp, C.c_int, vp, vp]

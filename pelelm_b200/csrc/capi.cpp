@@ -155,6 +155,12 @@ int plm_reactor_create(plm_reactor** out, const char* mechanism, const char* int
 
 int plm_num_species(const plm_reactor* r) { return r ? r->tables->ns : 0; }
 
+const char* plm_species_name(const plm_reactor* r, int k)
+{
+  if (!r || k < 0 || k >= r->tables->ns) return "";
+  return r->tables->species[k];
+}
+
 int plm_reactor_init(plm_reactor* r, int reactor_type, double rtol, double atol, int max_order, int max_nls_iters,
                      int clean_init_massfrac, const char* solve_type, int rk64_guess, int rk64_min, int rk64_max)
 {
