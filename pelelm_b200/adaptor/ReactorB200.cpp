@@ -7,6 +7,12 @@
 
 namespace pele {
 namespace physics {
+
+// The two classes are header-only, so no translation unit would otherwise emit Register<T>::registered (the static
+// whose initialiser inserts the creator into the factory table, Factory.H:96-130): instantiate them here.
+template struct Factory<reactions::ReactorBase>::Register<reactions::ReactorCvodeB200>;
+template struct Factory<reactions::ReactorBase>::Register<reactions::ReactorRK64B200>;
+
 namespace reactions {
 
 namespace {

@@ -1,7 +1,9 @@
 // Per-cell variable-order (1..5) variable-step BDF integrator with modified Newton and dense LU,
 // one warp per cell: state vectors are lane-resident (component i = lane + 32*slot), the Nordsieck
-// array, the Newton matrix and its saved Jacobian live in the warp's shared memory, all step-size /
-// order decisions are taken on warp-uniform scalars (butterfly reductions give every lane the same bits).
+// array and the Newton matrix live in the warp's shared memory (compile-time layout, chem_warp.cuh Lay<>), the saved
+// Jacobian in a per-warp global scratch (L2 resident; touched only at the ~50 linear-solver setups per cell), the
+// step-size / order scalars and the BDF coefficient arrays in registers (every lane computes the same bits:
+// butterfly reductions), so all control flow is warp-uniform and needs no broadcasts.
 //
 // Behavioural specification = SUNDIALS CVODE 6.2.0 as configured by PelePhysics' CPU ReactorCvode
 // (constants cvode_impl.h:57-130, cvode.c:111-118, cvode_nls.c:29-31,
@@ -12,6 +14,8 @@
 //   cvComputeEtaqm1/qp1 :3299/:3318 | cvChooseEta :3347 | CVodeGetDky :1490
 //   SUNNonlinSolSolve_Newton sunnonlinsol_newton.c:187 | cvNlsConvTest/Residual/LSetup cvode_nls.c:251-388
 //   cvLsSetup/cvLsLinSys/cvLsSolve cvode_ls.c:1270-1720 | denseGETRF/GETRS sundials_dense.c:135-232
+// One deliberate arithmetic difference: the linear-solver setup forms the inverse of the Newton matrix (Gauss-Jordan
+// with the same partial-pivoting rule) and each Newton iteration is a mat-vec, see gjinv_warp below.
 #pragma once
 #include <cfloat>
 
@@ -24,7 +28,6 @@ struct BdfOpts {
   int qmax;      // cvode.max_order
   int maxcor;    // ode.max_nls_iters
   int ajac;      // 1 analytic Jacobian (denseAJ_direct), 0 difference quotient (dense_direct)
-  int use_typ;   // atol_i = typ_i * atol
   int mxstep;    // 10000 (ReactorCvode.cpp:276)
   int maxnef;    // 100   (ReactorCvode.cpp:267)
   int msbj;      // 100   (ReactorCvode.cpp:285)
@@ -49,7 +52,7 @@ enum { NLS_SUCCESS = 0, NLS_CONV_RECVR = 902 };
 }  // namespace cvc
 
 // SUNRpowerR (sundials_math.c:56): pow(base, e) for base > 0 else 0; exp(e*log(base)) keeps the device code call-free
-__device__ __forceinline__ double rpowR(double base, double e) { return base <= 0.0 ? 0.0 : exp(e * log(base)); }
+__device__ __noinline__ double rpowR(double base, double e) { return base <= 0.0 ? 0.0 : exp(e * log(base)); }
 __device__ __forceinline__ double rpowI(double base, int e)
 {
   double prod = 1.0;
@@ -59,14 +62,26 @@ __device__ __forceinline__ double rpowI(double base, int e)
   return prod;
 }
 
-// ---- dense LU with partial pivoting on the warp's shared-memory matrix (row-major, lane = row) ----
-template <int NSLOT>
-__device__ __forceinline__ int getrf_warp(double* A, int n, int ld, int* perm, int lane)
+// ---- Newton matrix: in-place Gauss-Jordan inverse with partial pivoting (row-major, lane = row) ----
+// CVODE factors A = I - gamma*J once per setup (denseGETRF) and then runs two triangular solves per Newton iteration
+// (denseGETRS); with ~16 iterations per setup and one warp per system the triangular solves are ~44 dependent
+// shuffle/FMA steps each. Here the setup forms W = (P A)^-1 (same pivot rule as denseGETRF: first largest |a_ik|,
+// sundials_dense.c:150-152) and every Newton iteration is one dense mat-vec x = W (P b): no dependent chain, no
+// predicates. The iteration matrix is an approximation to begin with (stale J, stale gamma); the converged Newton
+// solution does not depend on how W b is rounded.
+template <class L>
+__device__ __noinline__ int gjinv_warp()
 {
+  constexpr int NSLOT = L::NSLOT, n = L::N, ld = L::LD;
+  double* wb = warp_base<L>();
+  double* A = wb + L::A;
+  int* perm = reinterpret_cast<int*>(wb + L::PERM);
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s)
     if (lane + 32 * s < n) perm[lane + 32 * s] = lane + 32 * s;
   __syncwarp();
+#pragma unroll 1
   for (int k = 0; k < n; ++k) {
     double v = -1.0;
     int idx = 0x7fffffff;
@@ -75,7 +90,7 @@ __device__ __forceinline__ int getrf_warp(double* A, int n, int ld, int* perm, i
       const int i = lane + 32 * s;
       if (i >= k && i < n) {
         const double a = fabs(A[i * ld + k]);
-        if (a > v) {  // strict: first occurrence wins (sundials_dense.c:150-152)
+        if (a > v) {  // strict: first occurrence wins
           v = a;
           idx = i;
         }
@@ -92,32 +107,30 @@ __device__ __forceinline__ int getrf_warp(double* A, int n, int ld, int* perm, i
     }
     const int l = idx;
     if (v == 0.0) return k + 1;
-    if (l != k) {
-      for (int j = lane; j < n; j += 32) {
-        const double t = A[l * ld + j];
-        A[l * ld + j] = A[k * ld + j];
-        A[k * ld + j] = t;
-      }
-      if (lane == 0) {
-        const int t = perm[l];
-        perm[l] = perm[k];
-        perm[k] = t;
-      }
-      __syncwarp();
+    const double pivinv = 1.0 / A[l * ld + k];
+    __syncwarp();
+    // swap rows l and k and scale the pivot row: lane = column
+    for (int j = lane; j < n; j += 32) {
+      const double t = A[l * ld + j];
+      if (l != k) A[l * ld + j] = A[k * ld + j];
+      A[k * ld + j] = (j == k) ? pivinv : t * pivinv;
     }
-    const double mult = 1.0 / A[k * ld + k];
+    if (lane == 0 && l != k) {
+      const int t = perm[l];
+      perm[l] = perm[k];
+      perm[k] = t;
+    }
+    __syncwarp();
+    const double* rk = A + k * ld;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       const int i = lane + 32 * s;
-      if (i > k && i < n) {
+      if (i != k && i < n) {
         double* row = A + i * ld;
-        const double* rk = A + k * ld;
-        const double mi = row[k] * mult;
-        row[k] = mi;
-        for (int j = k + 1; j < n; ++j) {
-          const double a_kj = rk[j];
-          row[j] -= a_kj * mi;
-        }
+        const double f = row[k];
+        row[k] = 0.0;
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) row[j] -= rk[j] * f;
       }
     }
     __syncwarp();
@@ -125,78 +138,63 @@ __device__ __forceinline__ int getrf_warp(double* A, int n, int ld, int* perm, i
   return 0;
 }
 
-template <int NSLOT>
-__device__ __forceinline__ double bcast_comp(const double (&b)[NSLOT], int k)
+// x = W (P b): in wb[FB] = b (every lane its own components), out = x of the lane's components.
+template <class L>
+__device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::NSLOT])
 {
-  double v = b[0];
-#pragma unroll
-  for (int s = 1; s < NSLOT; ++s)
-    if ((k >> 5) == s) v = b[s];
-  return __shfl_sync(kFull, v, k & 31);
-}
-
-// b <- A^{-1} b with the factors of getrf_warp; scratch holds >= n doubles of shared memory
-template <int NSLOT>
-__device__ __forceinline__ void getrs_warp(const double* A, int n, int ld, const int* perm, double (&b)[NSLOT],
-                                           double* scratch, int lane)
-{
+  constexpr int NSLOT = L::NSLOT, n = L::N, ld = L::LD;
+  const int* perm = reinterpret_cast<const int*>(wb + L::PERM);
   __syncwarp();
+  double t[NSLOT];
 #pragma unroll
-  for (int s = 0; s < NSLOT; ++s)
-    if (lane + 32 * s < n) scratch[lane + 32 * s] = b[s];
+  for (int s = 0; s < NSLOT; ++s) t[s] = (lane + 32 * s < n) ? wb[L::FB + perm[lane + 32 * s]] : 0.0;
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) wb[L::YB + lane + 32 * s] = t[s];  // YB is free between right-hand-side calls
   __syncwarp();
+  const double* pb = wb + L::YB;
 #pragma unroll
-  for (int s = 0; s < NSLOT; ++s)
-    if (lane + 32 * s < n) b[s] = scratch[perm[lane + 32 * s]];
-  for (int k = 0; k < n - 1; ++k) {
-    const double bk = bcast_comp<NSLOT>(b, k);
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-      const int i = lane + 32 * s;
-      if (i > k && i < n) b[s] -= A[i * ld + k] * bk;
+  for (int s = 0; s < NSLOT; ++s) {
+    const double* row = wb + L::A + min(lane + 32 * s, n - 1) * ld;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 11
+    for (int j = 0; j + 1 < n; j += 2) {
+      a0 = fma(row[j], pb[j], a0);
+      a1 = fma(row[j + 1], pb[j + 1], a1);
     }
+    if (n & 1) a0 = fma(row[n - 1], pb[n - 1], a0);
+    x[s] = a0 + a1;
   }
-  for (int k = n - 1; k > 0; --k) {
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s)
-      if (lane + 32 * s == k) b[s] /= A[k * ld + k];
-    const double bk = bcast_comp<NSLOT>(b, k);
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-      const int i = lane + 32 * s;
-      if (i < k) b[s] -= A[i * ld + k] * bk;
-    }
-  }
-  if (lane == 0) b[0] /= A[0];
   __syncwarp();
 }
 
-template <int NSLOT>
+template <class L>
 struct BdfWarp {
-  const DevMech& m;
-  const WarpMem& wm;
+  static constexpr int NSLOT = L::NSLOT, n = L::N, NP = L::NP, QM = L::QM, ld = L::LD;
   const BdfOpts& o;
   const int lane;
-  const int n, P;
-  double rhoe_init, rhoesrc;
-  double src[NSLOT], atolv[NSLOT];
+  double* const wb;
+  double* const Jsave;  // [n*ld] per-warp global scratch
+  double atolv[NSLOT];
   double ewt[NSLOT], acor[NSLOT], yv[NSLOT], ft[NSLOT], dl[NSLOT], tv[NSLOT];
+  double tau[QM + 1], lc[QM + 1], tq[6];
   double tn, h, hprime, hscale, eta, etamax;
-  int q, qprime, L, qwait, indx_acor;
+  int q, qprime, L_, qwait, indx_acor;
   double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
   int nst, nfe, ncfn, netf, nni, nsetups, nje, nstlp, nstlj;
   int jcur, convfail;
 
-  __device__ BdfWarp(const DevMech& m_, const WarpMem& wm_, const BdfOpts& o_, int lane_)
-      : m(m_), wm(wm_), o(o_), lane(lane_), n(m_.n), P(m_.nsp_pad)
-  {
-  }
+  __device__ BdfWarp(const BdfOpts& o_, int lane_, double* wb_, double* js) : o(o_), lane(lane_), wb(wb_), Jsave(js) {}
 
   __device__ __forceinline__ bool valid(int s) const { return lane + 32 * s < n; }
-  __device__ __forceinline__ double& zn(int j, int s) const { return wm.zn[j * P + lane + 32 * s]; }
-  __device__ __forceinline__ double& tau(int i) const { return wm.sm[i]; }
-  __device__ __forceinline__ double& tq(int i) const { return wm.sm[8 + i]; }
-  __device__ __forceinline__ double& l(int i) const { return wm.sm[16 + i]; }
+  __device__ __forceinline__ double& zn(int j, int s) const { return wb[L::ZN + j * NP + lane + 32 * s]; }
+  template <int SZ>
+  static __device__ __forceinline__ double sel(const double (&a)[SZ], int i)
+  {
+    double v = a[0];
+#pragma unroll
+    for (int k = 1; k < SZ; ++k) v = (i == k) ? a[k] : v;
+    return v;
+  }
 
   __device__ __forceinline__ double wrms(const double (&x)[NSLOT], const double (&w)[NSLOT]) const
   {
@@ -235,22 +233,28 @@ struct BdfWarp {
     }
     return __any_sync(kFull, bad) == 0;
   }
+  // ydot = f(t, y) through the shared-memory argument buffers of rhs_warp
   __device__ __forceinline__ void f(double t, const double (&y)[NSLOT], double (&ydot)[NSLOT])
   {
-    rhs_warp<NSLOT>(m, wm, lane, t, y, src, rhoe_init, rhoesrc, ydot);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) wb[L::YB + lane + 32 * s] = y[s];
+    __syncwarp();
+    rhs_warp<L>(t);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) ydot[s] = wb[L::FB + lane + 32 * s];
     nfe++;
   }
 
   // cvLsDenseDQJac (cvode_ls.c:1034-1107): fy = f(tn, yv) in ft
   __device__ __forceinline__ void dq_jac(double* Jm)
   {
-    const int ld = wm.ld;
     const double uround = DBL_EPSILON, srur = sqrt(uround);
     const double fnorm = wrms(ft, ewt);
     const double minInc = (fnorm != 0.0) ? (1000.0 * fabs(h) * uround * n * fnorm) : 1.0;
     double ysave[NSLOT], ft2[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) ysave[s] = yv[s];
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
       double inc_l = 0.0;
 #pragma unroll
@@ -260,8 +264,7 @@ struct BdfWarp {
           yv[s] += inc_l;
         }
       const double inc = __shfl_sync(kFull, inc_l, j & 31);
-      rhs_warp<NSLOT>(m, wm, lane, tn, yv, src, rhoe_init, rhoesrc, ft2);
-      nfe++;
+      f(tn, yv, ft2);
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) yv[s] = ysave[s];
       const double inc_inv = 1.0 / inc;
@@ -275,32 +278,38 @@ struct BdfWarp {
   // cvNlsLSetup + cvLsSetup + cvLsLinSys + dense factorisation
   __device__ __forceinline__ int lsetup()
   {
-    const int ld = wm.ld;
+    double* A = wb + L::A;
     const double dgamma = fabs((gamma / gammap) - 1.0);
     const bool jbad = (nst == 0) || (nst >= nstlj + o.msbj) ||
                       ((convfail == cvc::FAIL_BAD_J) && (dgamma < cvc::DGMAX_JBAD)) || (convfail == cvc::FAIL_OTHER);
     __syncwarp();
     if (jbad) {
       jcur = 1;
-      if (o.ajac) jac_warp<NSLOT>(m, wm, lane, yv, wm.A);
-      else dq_jac(wm.A);
-      for (int e = lane; e < n * ld; e += 32) wm.J[e] = wm.A[e];
+      if (o.ajac) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) wb[L::YB + lane + 32 * s] = yv[s];
+        __syncwarp();
+        jac_warp<L>(A);
+      } else {
+        dq_jac(A);
+      }
+      for (int e = lane; e < n * ld; e += 32) Jsave[e] = A[e];
       nje++;
       nstlj = nst;
     } else {
       jcur = 0;
-      for (int e = lane; e < n * ld; e += 32) wm.A[e] = wm.J[e];
+      for (int e = lane; e < n * ld; e += 32) A[e] = Jsave[e];
     }
     __syncwarp();
     const double c = -gamma;
     for (int e = lane; e < n * ld; e += 32) {
       const int i = e / ld, j = e - i * ld;
-      double a = wm.A[e] * c;
+      double a = A[e] * c;
       if (i == j) a += 1.0;
-      wm.A[e] = a;
+      A[e] = a;
     }
     __syncwarp();
-    const int ier = getrf_warp<NSLOT>(wm.A, n, ld, wm.perm, lane);
+    const int ier = gjinv_warp<L>();
     nsetups++;
     gamrat = 1.0;
     gammap = gamma;
@@ -329,21 +338,31 @@ struct BdfWarp {
   {
     bool jbadflag = false;
     int nls_jcur = 0, retval;
+#pragma unroll 1
     for (;;) {
-      residual();
+      bool need_res = true;
       retval = cvc::NLS_SUCCESS;
-      if (callSetup) {
-        if (jbadflag) convfail = cvc::FAIL_BAD_J;
-        retval = lsetup();
-        nls_jcur = jcur;
-        if (retval != cvc::NLS_SUCCESS) return retval;
-      }
       int mit = 0;
+      bool setup_failed = false;
+#pragma unroll 1
       for (;;) {
+        if (need_res) residual();  // single call site of the residual / right-hand side inside the Newton loop
+        if (mit == 0 && callSetup) {
+          if (jbadflag) convfail = cvc::FAIL_BAD_J;
+          retval = lsetup();
+          nls_jcur = jcur;
+          callSetup = false;
+          if (retval != cvc::NLS_SUCCESS) {
+            setup_failed = true;
+            break;
+          }
+        }
         nni++;
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) dl[s] = -dl[s];
-        getrs_warp<NSLOT>(wm.A, n, wm.ld, wm.perm, dl, wm.q, lane);
+        for (int s = 0; s < NSLOT; ++s) wb[L::FB + lane + 32 * s] = -dl[s];
+        solve_warp<L>(wb, lane, dl);
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) dl[s] = valid(s) ? dl[s] : 0.0;
         if (gamrat != 1.0) {
           const double sc = 2.0 / (1.0 + gamrat);
 #pragma unroll
@@ -353,7 +372,7 @@ struct BdfWarp {
         for (int s = 0; s < NSLOT; ++s) acor[s] = valid(s) ? acor[s] + dl[s] : 0.0;
         const double del = wrms(dl, ewt);
         if (mit > 0) crate = fmax(cvc::CRDOWN * crate, del / delp);
-        const double dcon = del * fmin(1.0, crate) / tq(4);
+        const double dcon = del * fmin(1.0, crate) / tq[4];
         if (dcon <= 1.0) {
           acnrm = (mit == 0) ? del : wrms(acor, ewt);
           return cvc::NLS_SUCCESS;
@@ -368,8 +387,9 @@ struct BdfWarp {
           retval = cvc::NLS_CONV_RECVR;
           break;
         }
-        residual();
+        need_res = true;
       }
+      if (setup_failed) return retval;
       if ((retval > 0) && !nls_jcur) {
         callSetup = true;
         jbadflag = true;
@@ -385,11 +405,14 @@ struct BdfWarp {
   __device__ __forceinline__ void rescale()
   {
     double fac = eta;
-    for (int j = 1; j <= q; j++) {
 #pragma unroll
-      for (int s = 0; s < NSLOT; ++s)
-        if (valid(s)) zn(j, s) *= fac;
-      fac = eta * fac;
+    for (int j = 1; j <= QM; j++) {
+      if (j <= q) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (valid(s)) zn(j, s) *= fac;
+        fac = eta * fac;
+      }
     }
     h = hscale * eta;
     hscale = h;
@@ -397,61 +420,69 @@ struct BdfWarp {
 
   __device__ __forceinline__ void increase_bdf()
   {
-    __syncwarp();
-    if (lane == 0) {  // scalar recurrences are done by one lane on the shared coefficient arrays
-      double alpha0, alpha1, prod, xi, xiold, hsum;
-      for (int i = 0; i <= o.qmax; i++) l(i) = 0.0;
-      l(2) = alpha1 = prod = xiold = 1.0;
-      alpha0 = -1.0;
-      hsum = hscale;
-      if (q > 1) {
-        for (int j = 1; j < q; j++) {
-          hsum += tau(j + 1);
-          xi = hsum / hscale;
-          prod *= xi;
-          alpha0 -= 1.0 / (j + 1);
-          alpha1 += 1.0 / xi;
-          for (int i = j + 2; i >= 2; i--) l(i) = l(i) * xiold + l(i - 1);
-          xiold = xi;
-        }
-      }
-      wm.sm[24] = (-alpha0 - alpha1) / prod;
-    }
-    __syncwarp();
-    const double A1 = wm.sm[24];
+    double alpha0, alpha1, prod, xi, xiold, hsum;
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s)
-      if (valid(s)) zn(L, s) = A1 * zn(indx_acor, s);
-    if (q > 1)
-      for (int j = 2; j <= q; j++) {
-        const double lj = l(j);
+    for (int i = 0; i <= QM; i++) lc[i] = 0.0;
+    lc[2] = alpha1 = prod = xiold = 1.0;
+    alpha0 = -1.0;
+    hsum = hscale;
+#pragma unroll
+    for (int j = 1; j < QM; j++) {
+      if (j < q) {
+        hsum += tau[j + 1];
+        xi = hsum / hscale;
+        prod *= xi;
+        alpha0 -= 1.0 / (j + 1);
+        alpha1 += 1.0 / xi;
+#pragma unroll
+        for (int i = j + 2; i >= 2; i--)
+          if (i <= QM) lc[i] = lc[i] * xiold + lc[i - 1];
+        xiold = xi;
+      }
+    }
+    const double A1 = (-alpha0 - alpha1) / prod;
+    // zn[L] = A1 * zn[indx_acor]; indx_acor == qmax always (cvode.c:3192)
+#pragma unroll
+    for (int jl = 2; jl <= QM; ++jl) {
+      if (jl == L_) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
-          if (valid(s)) zn(j, s) = lj * zn(L, s) + zn(j, s);
+          if (valid(s)) zn(jl, s) = A1 * wb[L::ZN + indx_acor * NP + lane + 32 * s];
       }
+    }
+#pragma unroll
+    for (int j = 2; j <= QM; j++) {
+      if (j <= q) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (valid(s)) zn(j, s) = lc[j] * wb[L::ZN + L_ * NP + lane + 32 * s] + zn(j, s);
+      }
+    }
   }
   __device__ __forceinline__ void decrease_bdf()
   {
-    __syncwarp();
-    if (lane == 0) {
-      double hsum, xi;
-      for (int i = 0; i <= o.qmax; i++) l(i) = 0.0;
-      l(2) = 1.0;
-      hsum = 0.0;
-      for (int j = 1; j <= q - 2; j++) {
-        hsum += tau(j);
+    double hsum, xi;
+#pragma unroll
+    for (int i = 0; i <= QM; i++) lc[i] = 0.0;
+    lc[2] = 1.0;
+    hsum = 0.0;
+#pragma unroll
+    for (int j = 1; j <= QM - 2; j++) {
+      if (j <= q - 2) {
+        hsum += tau[j];
         xi = hsum / hscale;
-        for (int i = j + 2; i >= 2; i--) l(i) = l(i) * xi + l(i - 1);
+#pragma unroll
+        for (int i = j + 2; i >= 2; i--) lc[i] = lc[i] * xi + lc[i - 1];
       }
     }
-    __syncwarp();
-    if (q > 2)
-      for (int j = 2; j < q; j++) {
-        const double lj = l(j);
+#pragma unroll
+    for (int j = 2; j < QM; j++) {
+      if (j < q) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
-          if (valid(s)) zn(j, s) = -lj * zn(q, s) + zn(j, s);
+          if (valid(s)) zn(j, s) = -lc[j] * wb[L::ZN + q * NP + lane + 32 * s] + zn(j, s);
       }
+    }
   }
   __device__ __forceinline__ void adjust_order(int deltaq)
   {
@@ -464,78 +495,89 @@ struct BdfWarp {
     if (qprime != q) {
       adjust_order(qprime - q);
       q = qprime;
-      L = q + 1;
-      qwait = L;
+      L_ = q + 1;
+      qwait = L_;
     }
     rescale();
+  }
+  template <int SIGN>
+  __device__ __forceinline__ void pascal()
+  {
+#pragma unroll
+    for (int k = 1; k <= QM; k++) {
+      if (k <= q) {
+#pragma unroll
+        for (int j = QM; j >= k; j--) {
+          if (j <= q) {
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+              if (valid(s)) zn(j - 1, s) = (SIGN > 0) ? zn(j - 1, s) + zn(j, s) : zn(j - 1, s) - zn(j, s);
+          }
+        }
+      }
+    }
   }
   __device__ __forceinline__ void predict()
   {
     tn += h;
-    for (int k = 1; k <= q; k++)
-      for (int j = q; j >= k; j--) {
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-          if (valid(s)) zn(j - 1, s) = zn(j - 1, s) + zn(j, s);
-      }
+    pascal<1>();
   }
   __device__ __forceinline__ void restore(double saved_t)
   {
     tn = saved_t;
-    for (int k = 1; k <= q; k++)
-      for (int j = q; j >= k; j--) {
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-          if (valid(s)) zn(j - 1, s) = zn(j - 1, s) - zn(j, s);
-      }
+    pascal<-1>();
   }
   __device__ __forceinline__ void set_bdf()
   {
-    __syncwarp();
-    if (lane == 0) {
-      double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
-      l(0) = l(1) = xi_inv = xistar_inv = 1.0;
-      for (int i = 2; i <= q; i++) l(i) = 0.0;
-      alpha0 = alpha0_hat = -1.0;
-      hsum = h;
-      if (q > 1) {
-        for (int j = 2; j < q; j++) {
-          hsum += tau(j - 1);
+    double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
+    lc[0] = lc[1] = xi_inv = xistar_inv = 1.0;
+#pragma unroll
+    for (int i = 2; i <= QM; i++) lc[i] = 0.0;
+    alpha0 = alpha0_hat = -1.0;
+    hsum = h;
+    if (q > 1) {
+#pragma unroll
+      for (int j = 2; j < QM; j++) {
+        if (j < q) {
+          hsum += tau[j - 1];
           xi_inv = h / hsum;
           alpha0 -= 1.0 / j;
-          for (int i = j; i >= 1; i--) l(i) += l(i - 1) * xi_inv;
+#pragma unroll
+          for (int i = j; i >= 1; i--) lc[i] += lc[i - 1] * xi_inv;
         }
-        alpha0 -= 1.0 / q;
-        xistar_inv = -l(1) - alpha0;
-        hsum += tau(q - 1);
-        xi_inv = h / hsum;
-        alpha0_hat = -l(1) - xi_inv;
-        for (int i = q; i >= 1; i--) l(i) += l(i - 1) * xistar_inv;
       }
-      const double A1 = 1.0 - alpha0_hat + alpha0;
-      const double A2 = 1.0 + q * A1;
-      tq(2) = fabs(A1 / (alpha0 * A2));
-      tq(5) = fabs(A2 * xistar_inv / (l(q) * xi_inv));
-      if (qwait == 1) {
-        if (q > 1) {
-          const double C = xistar_inv / l(q);
-          const double A3 = alpha0 + 1.0 / q;
-          const double A4 = alpha0_hat + xi_inv;
-          const double Cpinv = (1.0 - A4 + A3) / A3;
-          tq(1) = fabs(C * Cpinv);
-        } else
-          tq(1) = 1.0;
-        hsum += tau(q);
-        xi_inv = h / hsum;
-        const double A5 = alpha0 - (1.0 / (q + 1));
-        const double A6 = alpha0_hat - xi_inv;
-        const double Cppinv = (1.0 - A6 + A5) / A2;
-        tq(3) = fabs(Cppinv / (xi_inv * (q + 2) * A5));
-      }
-      tq(4) = cvc::CORTES / tq(2);
+      alpha0 -= 1.0 / q;
+      xistar_inv = -lc[1] - alpha0;
+      hsum += sel(tau, q - 1);
+      xi_inv = h / hsum;
+      alpha0_hat = -lc[1] - xi_inv;
+#pragma unroll
+      for (int i = QM; i >= 1; i--)
+        if (i <= q) lc[i] += lc[i - 1] * xistar_inv;
     }
-    __syncwarp();
-    rl1 = 1.0 / l(1);
+    const double lq = sel(lc, q);
+    const double A1 = 1.0 - alpha0_hat + alpha0;
+    const double A2 = 1.0 + q * A1;
+    tq[2] = fabs(A1 / (alpha0 * A2));
+    tq[5] = fabs(A2 * xistar_inv / (lq * xi_inv));
+    if (qwait == 1) {
+      if (q > 1) {
+        const double C = xistar_inv / lq;
+        const double A3 = alpha0 + 1.0 / q;
+        const double A4 = alpha0_hat + xi_inv;
+        const double Cpinv = (1.0 - A4 + A3) / A3;
+        tq[1] = fabs(C * Cpinv);
+      } else
+        tq[1] = 1.0;
+      hsum += sel(tau, q);
+      xi_inv = h / hsum;
+      const double A5 = alpha0 - (1.0 / (q + 1));
+      const double A6 = alpha0_hat - xi_inv;
+      const double Cppinv = (1.0 - A6 + A5) / A2;
+      tq[3] = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+    }
+    tq[4] = cvc::CORTES / tq[2];
+    rl1 = 1.0 / lc[1];
     gamma = h * rl1;
     if (nst == 0) gammap = gamma;
     gamrat = (nst > 0) ? gamma / gammap : 1.0;
@@ -570,7 +612,7 @@ struct BdfWarp {
 
   __device__ __forceinline__ int do_error_test(int& nflag, double saved_t, int& nef, double& dsm)
   {
-    dsm = acnrm * tq(2);
+    dsm = acnrm * tq[2];
     if (dsm <= 1.0) return 0;
     nef++;
     netf++;
@@ -579,7 +621,7 @@ struct BdfWarp {
     if (nef == o.maxnef) return cvc::CV_ERR_FAILURE;
     etamax = 1.0;
     if (nef <= cvc::MXNEF1) {
-      eta = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L) + cvc::ADDON);
+      eta = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L_) + cvc::ADDON);
       eta = fmax(cvc::ETA_MIN_EF, eta);
       if (nef >= cvc::SMALL_NEF) eta = fmin(eta, cvc::ETA_MAX_EF);
       rescale();
@@ -588,9 +630,9 @@ struct BdfWarp {
     if (q > 1) {
       eta = cvc::ETA_MIN_EF;
       adjust_order(-1);
-      L = q;
+      L_ = q;
       q--;
-      qwait = L;
+      qwait = L_;
       rescale();
       return cvc::TRY_AGAIN;
     }
@@ -610,25 +652,25 @@ struct BdfWarp {
   __device__ __forceinline__ void complete_step()
   {
     nst++;
-    __syncwarp();
-    if (lane == 0) {
-      for (int i = q; i >= 2; i--) tau(i) = tau(i - 1);
-      if ((q == 1) && (nst > 1)) tau(2) = tau(1);
-      tau(1) = h;
-    }
-    __syncwarp();
-    for (int j = 0; j <= q; j++) {
-      const double lj = l(j);
 #pragma unroll
-      for (int s = 0; s < NSLOT; ++s)
-        if (valid(s)) zn(j, s) = lj * acor[s] + zn(j, s);
+    for (int i = QM; i >= 2; i--)
+      if (i <= q) tau[i] = tau[i - 1];
+    if ((q == 1) && (nst > 1)) tau[2] = tau[1];
+    tau[1] = h;
+#pragma unroll
+    for (int j = 0; j <= QM; j++) {
+      if (j <= q) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+          if (valid(s)) zn(j, s) = lc[j] * acor[s] + zn(j, s);
+      }
     }
     qwait--;
     if ((qwait == 1) && (q != o.qmax)) {
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
-        if (valid(s)) zn(o.qmax, s) = acor[s];
-      saved_tq5 = tq(5);
+        if (valid(s)) wb[L::ZN + o.qmax * NP + lane + 32 * s] = acor[s];
+      saved_tq5 = tq[5];
       indx_acor = o.qmax;
     }
   }
@@ -654,7 +696,7 @@ struct BdfWarp {
       eta = 1.0;
       return;
     }
-    const double etaq = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L) + cvc::ADDON);
+    const double etaq = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L_) + cvc::ADDON);
     if (qwait != 0) {
       eta = etaq;
       qprime = q;
@@ -664,15 +706,23 @@ struct BdfWarp {
     qwait = 2;
     double etaqm1 = 0.0, etaqp1 = 0.0;
     if (q > 1) {
-      const double ddn = wrms_zn(q) * tq(1);
+      double a = 0.0;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (valid(s)) {
+          const double p = wb[L::ZN + q * NP + lane + 32 * s] * ewt[s];
+          a += p * p;
+        }
+      const double ddn = sqrt(warp_sum(a) / n) * tq[1];
       etaqm1 = 1.0 / (rpowR(cvc::BIAS1 * ddn, 1.0 / q) + cvc::ADDON);
     }
     if (q != o.qmax && saved_tq5 != 0.0) {
-      const double cquot = (tq(5) / saved_tq5) * rpowI(h / tau(2), L);
+      const double cquot = (tq[5] / saved_tq5) * rpowI(h / tau[2], L_);
 #pragma unroll
-      for (int s = 0; s < NSLOT; ++s) tv[s] = valid(s) ? -cquot * zn(o.qmax, s) + acor[s] : 0.0;
-      const double dup = wrms(tv, ewt) * tq(3);
-      etaqp1 = 1.0 / (rpowR(cvc::BIAS3 * dup, 1.0 / (L + 1)) + cvc::ADDON);
+      for (int s = 0; s < NSLOT; ++s)
+        tv[s] = valid(s) ? -cquot * wb[L::ZN + o.qmax * NP + lane + 32 * s] + acor[s] : 0.0;
+      const double dup = wrms(tv, ewt) * tq[3];
+      etaqp1 = 1.0 / (rpowR(cvc::BIAS3 * dup, 1.0 / (L_ + 1)) + cvc::ADDON);
     }
     const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
     if ((etam > cvc::ETA_MIN_FX) && (etam < cvc::ETA_MAX_FX)) {
@@ -689,7 +739,7 @@ struct BdfWarp {
       qprime = q + 1;
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
-        if (valid(s)) zn(o.qmax, s) = acor[s];
+        if (valid(s)) wb[L::ZN + o.qmax * NP + lane + 32 * s] = acor[s];
     }
     set_eta();
   }
@@ -701,6 +751,7 @@ struct BdfWarp {
     if ((nst > 0) && (hprime != h)) adjust_params();
     const double saved_t = tn;
     nflag = cvc::FIRST_CALL;
+#pragma unroll 1
     for (;;) {
       predict();
       set_bdf();
@@ -716,7 +767,7 @@ struct BdfWarp {
     complete_step();
     prepare_next_step(dsm);
     etamax = (nst <= cvc::SMALL_NST) ? cvc::ETA_MAX_ES : cvc::ETA_MAX_GS;
-    const double t2 = tq(2);
+    const double t2 = tq[2];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acor[s] *= t2;
     return 0;
@@ -749,6 +800,7 @@ struct BdfWarp {
       return 0;
     }
     double hnew = hg;
+#pragma unroll 1
     for (int count1 = 1; count1 <= cvc::MAX_ITERS; count1++) {
       const double hgs = hg * sign;
 #pragma unroll
@@ -780,8 +832,8 @@ struct BdfWarp {
   {
     tn = t0;
     q = 1;
-    L = 2;
-    qwait = L;
+    L_ = 2;
+    qwait = L_;
     etamax = cvc::ETA_MAX_FS;
     nst = nfe = ncfn = netf = nni = nsetups = nje = nstlp = nstlj = 0;
     saved_tq5 = 0.0;
@@ -794,16 +846,17 @@ struct BdfWarp {
     qprime = 1;
     gammap = gamma = gamrat = rl1 = 1.0;
     acnrm = 0.0;
-    __syncwarp();
-    if (lane < 24) wm.sm[lane] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= QM; ++i) tau[i] = lc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) tq[i] = 0.0;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       acor[s] = 0.0;
-      if (lane + 32 * s < P)
-        for (int j = 0; j <= o.qmax; ++j) zn(j, s) = 0.0;
+#pragma unroll
+      for (int j = 0; j <= QM; ++j) zn(j, s) = 0.0;
       if (valid(s)) zn(0, s) = yio[s];
     }
-    __syncwarp();
     int istate = 0;
     if (!ewtset()) {
       istate = cvc::CV_ILL_INPUT;
@@ -823,6 +876,7 @@ struct BdfWarp {
       for (int s = 0; s < NSLOT; ++s)
         if (valid(s)) zn(1, s) *= h;
       int nstloc = 0;
+#pragma unroll 1
       for (;;) {
         if (nst > 0 && !ewtset()) {
           istate = cvc::CV_ILL_INPUT;
@@ -852,10 +906,13 @@ struct BdfWarp {
       for (int s = 0; s < NSLOT; ++s) {
         if (valid(s)) {
           double z = 0.0;
-          for (int j = q; j >= 0; j--) {
-            double c = 1.0;
-            for (int i = 0; i < j; i++) c *= sfac;
-            z = (j == q) ? c * zn(j, s) : z + c * zn(j, s);
+#pragma unroll
+          for (int j = QM; j >= 0; j--) {
+            if (j <= q) {
+              double c = 1.0;
+              for (int i = 0; i < j; i++) c *= sfac;
+              z = (j == q) ? c * zn(j, s) : z + c * zn(j, s);
+            }
           }
           yio[s] = z;
         }

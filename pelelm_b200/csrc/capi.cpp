@@ -98,7 +98,6 @@ struct plm_reactor {
   double pending_ms = 0.0;  // kernel time of completed-but-unreported calls
   // cached launch configuration
   plm::LaunchCfg cfg{};
-  bool j_in_smem = true;
   int cfg_qmax = -1;
 };
 
@@ -210,27 +209,14 @@ int configure(plm_reactor* r)
 {
   if (r->cfg_qmax == r->opts.qmax) return PLM_OK;
   const plm::DevMech& m = r->mech.h;
-  const int qmax = (r->integ == plm::kIntegCvode) ? r->opts.qmax : 0;
-  int best_warps = 0;
-  for (int pass = 0; pass < 2 && best_warps == 0; ++pass) {
-    const bool jsm = (pass == 0);
-    for (int wpb : {4, 2, 1}) {
-      const size_t smem = plm::react_smem_bytes(m, qmax, jsm, wpb);
-      if (smem > 227 * 1024) continue;
-      const int occ = plm::react_occupancy(m, r->integ, wpb * 32, smem);
-      if (occ <= 0) continue;
-      // keeping J in shared memory is only worth it if it does not starve the SM of warps
-      if (jsm && occ * wpb < 8) continue;
-      if (occ * wpb > best_warps) {
-        best_warps = occ * wpb;
-        r->cfg.blocks = occ * r->num_sms;
-        r->cfg.threads = wpb * 32;
-        r->cfg.smem_bytes = smem;
-        r->j_in_smem = jsm;
-      }
-    }
-  }
-  if (best_warps == 0) return fail(PLM_ERR_CUDA, "no launch configuration fits in shared memory");
+  const int wpb = plm::kReactThreads / 32;
+  const size_t smem = plm::react_smem_bytes(m, r->integ, r->opts.qmax, wpb);
+  if (smem == 0 || smem > 227 * 1024) return fail(PLM_ERR_CUDA, "no launch configuration fits in shared memory");
+  const int occ = plm::react_occupancy(m, r->integ, r->opts.qmax, wpb * 32, smem);
+  if (occ <= 0) return fail(PLM_ERR_CUDA, "kernel cannot be resident (occupancy query failed)");
+  r->cfg.blocks = occ * r->num_sms;  // persistent grid: every resident CTA slot of every SM
+  r->cfg.threads = wpb * 32;
+  r->cfg.smem_bytes = smem;
   r->cfg_qmax = r->opts.qmax;
   return PLM_OK;
 }
@@ -243,7 +229,6 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
   int rc = configure(r);
   if (rc != PLM_OK) return rc;
   const plm::DevMech& m = r->mech.h;
-  a.ld = plm::ld_for(m);
   const int si = r->next_slot;
   r->next_slot = (r->next_slot + 1) % kSlots;
   CallSlot& sl = r->slot[si];
@@ -258,15 +243,15 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
   const int64_t warps_needed = (a.ncells + plm::kCellsPerGrab - 1) / plm::kCellsPerGrab;
   const int wpb = cfg.threads / 32;
   cfg.blocks = int(std::max<int64_t>(1, std::min<int64_t>(cfg.blocks, (warps_needed + wpb - 1) / wpb)));
-  if (!r->j_in_smem) {
+  {  // saved Jacobians: one (N+1) x LD matrix per resident warp (L2 resident; read/written only at linear-solver setups)
     const size_t nw = size_t(r->cfg.blocks) * wpb;
-    if (sl.jglobal.ensure(nw * m.n * a.ld * sizeof(double)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+    if (sl.jglobal.ensure(nw * plm::react_jsave_doubles(m) * sizeof(double)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
   }
   auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
   PLM_CUDA(cudaMemsetAsync(ctrl + si, 0, sizeof(unsigned long long), stream));
   PLM_CUDA(cudaEventRecord(sl.ev0, stream));
-  PLM_CUDA(plm::launch_react(m, r->opts, a, cfg, r->integ, ctrl + si, ctrl + kSlots, static_cast<int*>(sl.status.p),
-                             r->j_in_smem ? nullptr : static_cast<double*>(sl.jglobal.p), stream));
+  PLM_CUDA(plm::launch_react(m, r->mech.d, r->opts, a, cfg, r->integ, ctrl + si, ctrl + kSlots,
+                             static_cast<int*>(sl.status.p), static_cast<double*>(sl.jglobal.p), stream));
   PLM_CUDA(cudaEventRecord(sl.ev1, stream));
   sl.used = true;
   sl.ncells = a.ncells;
@@ -461,7 +446,7 @@ int plm_eval_rhs(plm_reactor* r, int ncells, double t, const double* y, const do
     if ((rc = stage_in(r->scratch[3], rYsrc, size_t(ncells) * ns, &ds, st, true))) return rc;
     if ((rc = stage_in(r->scratch[4], static_cast<double*>(nullptr), size_t(ncells) * n, &dout, st, false))) return rc;
   }
-  PLM_CUDA(plm::launch_rhs(r->mech.h, ncells, t, dy, de, des, ds, dout, st));
+  PLM_CUDA(plm::launch_rhs(r->mech.h, r->mech.d, ncells, t, dy, de, des, ds, dout, st));
   if (!dev) PLM_CUDA(cudaMemcpyAsync(ydot, dout, size_t(ncells) * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   PLM_CUDA(cudaStreamSynchronize(st));
   return PLM_OK;
@@ -480,7 +465,7 @@ int plm_eval_jac(plm_reactor* r, int ncells, const double* y, double* J, void* c
     if ((rc = stage_in(r->scratch[0], y, size_t(ncells) * n, &dy, st, true))) return rc;
     if ((rc = stage_in(r->scratch[5], static_cast<double*>(nullptr), size_t(ncells) * n * n, &dJ, st, false))) return rc;
   }
-  PLM_CUDA(plm::launch_jac(r->mech.h, ncells, dy, dJ, st));
+  PLM_CUDA(plm::launch_jac(r->mech.h, r->mech.d, ncells, dy, dJ, st));
   if (!dev) PLM_CUDA(cudaMemcpyAsync(J, dJ, size_t(ncells) * n * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   PLM_CUDA(cudaStreamSynchronize(st));
   return PLM_OK;

@@ -1,11 +1,14 @@
 // sm_100a kernels behind the C ABI (include/plm_chem.h).
 //
-//   react_kernel<NSLOT, INTEG>  persistent warps pull cells from a global queue (per-cell cost varies
+//   react_kernel<Lay, INTEG>    persistent warps pull cells from a global queue (per-cell cost varies
 //                               10x inside a box, SURVEY.md section 7 "Divergence"): gather the cell from
 //                               the FAB (box_flatten, ReactorUtils.H:76-136), invert h -> T, integrate
 //                               (BDF: bdf_warp.cuh, RK64: below), scatter back (box_unflatten :138-207)
 //   rhs_kernel / jac_kernel     one warp per cell, for the fKernelSpec / cJac parity tests
 //   box_cost_kernel             per-box sum of FC (PeleLM::getFuncCountDM PeleLM.cpp:5557-5571)
+//   dfma_peak_kernel            measured FP64 roofline denominator
+// Kernels are instantiated per mechanism (compile-time species / reaction counts fix the shared-memory layout and
+// let small loops unroll) and per maximum BDF order class (<= 2, <= 5).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -15,6 +18,8 @@
 
 namespace plm {
 
+static_assert(sizeof(DevMech) <= kHdr * sizeof(double), "DevMech must fit in the shared-memory header");
+
 // ---- ReactorRK64 (ReactorRK64.cpp:206-317; coefficients ReactorRK64.H:11-42), one warp per cell ----
 __constant__ double c_alpha_rk64[6] = {0.218150805229859, 0.256702469801519, 0.527402592007520,
                                        0.0484864267224467, 1.24517071533530, 0.412366034843237};
@@ -23,13 +28,12 @@ __constant__ double c_beta_rk64[6] = {-0.113554138044166, -0.215118587818400, -0
 __constant__ double c_err_rk64[6] = {-0.0554699315064507, 0.158481845574980, -0.0905918835751907,
                                      -0.219084567203338, 0.164022338959433, 0.0426421977505659};
 
-template <int NSLOT>
-__device__ __forceinline__ int rk64_warp(const DevMech& m, const WarpMem& wm, int lane, const ReactOpts& o,
-                                         double (&soln)[NSLOT], const double (&src)[NSLOT], double rhoe_init,
-                                         double rhoesrc, double time_init, double dt_react, int& nfe)
+template <class L>
+__device__ __forceinline__ int rk64_warp(double* wb, int lane, const ReactOpts& o, double (&soln)[L::NSLOT],
+                                         double time_init, double dt_react, int& nfe)
 {
+  constexpr int NSLOT = L::NSLOT, n = L::N;
   const double exp1 = 0.25, exp2 = 0.2, betaerr = 1.0, tinyval = 1e-50;
-  const int n = m.n;
   double carry[NSLOT], err[NSLOT], rhs[NSLOT];
   const double time_out = time_init + dt_react;
   double current_time = time_init;
@@ -39,11 +43,18 @@ __device__ __forceinline__ int rk64_warp(const DevMech& m, const WarpMem& wm, in
   const double dt_rk_min = dt_react / double(o.rk64_max);
   const double dt_rk_max = dt_react / double(o.rk64_min);
   int nsteps = 0;
+#pragma unroll 1
   while (current_time < time_out) {
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) err[s] = 0.0;
+#pragma unroll 1
     for (int stage = 0; stage < 6; stage++) {
-      rhs_warp<NSLOT>(m, wm, lane, current_time - time_init, soln, src, rhoe_init, rhoesrc, rhs);
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) wb[L::YB + lane + 32 * s] = soln[s];
+      __syncwarp();
+      rhs_warp<L>(current_time - time_init);
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) rhs[s] = wb[L::FB + lane + 32 * s];
       nfe++;
       const double ce = c_err_rk64[stage], ca = c_alpha_rk64[stage], cb = c_beta_rk64[stage];
 #pragma unroll
@@ -73,36 +84,24 @@ __device__ __forceinline__ int rk64_warp(const DevMech& m, const WarpMem& wm, in
   return nsteps;
 }
 
-// carve the warp's shared-memory area
-__device__ __forceinline__ WarpMem carve(double* base, const DevMech& m, int qmax, int ld, double* jglobal)
+// copy the mechanism descriptor into the shared-memory header and set the constant pad entries of the warp's area
+template <class L>
+__device__ __forceinline__ double* block_prologue(const DevMech* __restrict__ dm)
 {
-  WarpMem wm;
-  double* p = base;
-  wm.sc = p; p += m.nsp_pad;
-  wm.gk = p; p += m.nsp_pad;
-  wm.hk = p; p += m.nsp_pad;
-  wm.q = p; p += m.nr_pad;
-  wm.A = p; p += size_t(m.n) * ld;
-  if (jglobal) {
-    wm.J = jglobal;
-  } else {
-    wm.J = p; p += size_t(m.n) * ld;
+  extern __shared__ double smem_dyn[];
+  {
+    const int words = int(sizeof(DevMech) / sizeof(int));
+    const int* src = reinterpret_cast<const int*>(dm);
+    int* dst = reinterpret_cast<int*>(smem_dyn);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
   }
-  wm.zn = p; p += size_t(qmax + 1) * m.nsp_pad;
-  wm.sm = p; p += 32;
-  wm.perm = reinterpret_cast<int*>(p);
-  wm.ld = ld;
-  return wm;
-}
-
-__device__ __forceinline__ void init_pads(const DevMech& m, const WarpMem& wm, int lane)
-{
-  for (int k = m.ns + lane; k < m.nsp_pad; k += 32) {
-    wm.sc[k] = 1.0;  // unit concentration for unused reactant/product slots
-    wm.gk[k] = 0.0;
-    wm.hk[k] = 0.0;
-  }
+  double* wb = warp_base<L>();
+  const int lane = threadIdx.x & 31;
+  for (int e = lane; e < L::TOTAL; e += 32) wb[e] = 0.0;
   __syncwarp();
+  if (lane == 0) wb[L::CG + 2 * L::NS] = 1.0;  // unit concentration for unused reactant/product slots; g = h = 0
+  __syncthreads();
+  return wb;
 }
 
 __device__ __forceinline__ int64_t a4_off(const plm_a4d& a, int i, int j, int k)
@@ -110,25 +109,21 @@ __device__ __forceinline__ int64_t a4_off(const plm_a4d& a, int i, int j, int k)
   return int64_t(i - a.lo[0]) + int64_t(j - a.lo[1]) * a.jstride + int64_t(k - a.lo[2]) * a.kstride;
 }
 
-template <int NSLOT, int INTEG>
-__global__ void __launch_bounds__(kReactThreads) react_kernel(const DevMech m, const ReactOpts o, const BoxArgs a,
-                                                              unsigned long long* __restrict__ counter,
-                                                              unsigned long long* __restrict__ gstats,
-                                                              int* __restrict__ status, double* __restrict__ jglobal)
+template <class L, int INTEG>
+__global__ void __launch_bounds__(kReactThreads, 4)
+    react_kernel(const DevMech* __restrict__ dm, const ReactOpts o, const BoxArgs a, unsigned long long* __restrict__ counter,
+                 unsigned long long* __restrict__ gstats, int* __restrict__ status, double* __restrict__ jglobal)
 {
-  extern __shared__ double smem[];
+  constexpr int NSLOT = L::NSLOT, ns = L::NS, n = L::N;
+  double* wb = block_prologue<L>(dm);
+  const DevMech& m = smem_mech();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ns = m.ns, n = m.n;
-  const size_t wdoubles = warp_mem_doubles(n, m.nsp_pad, m.nr_pad, o.qmax, a.ld, jglobal == nullptr);
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
-  double* jg = jglobal ? jglobal + size_t(gwarp) * n * a.ld : nullptr;
-  const WarpMem wm = carve(smem + warp * wdoubles, m, o.qmax, a.ld, jg);
-  init_pads(m, wm, lane);
 
   BdfOpts bo;
   bo.rtol = o.rtol; bo.atol = o.atol; bo.qmax = o.qmax; bo.maxcor = o.maxcor; bo.ajac = o.ajac;
-  bo.use_typ = o.use_typ; bo.mxstep = 10000; bo.maxnef = 100; bo.msbj = 100;
-  BdfWarp<NSLOT> bdf(m, wm, bo, lane);
+  bo.mxstep = 10000; bo.maxnef = 100; bo.msbj = 100;
+  BdfWarp<L> bdf(bo, lane, wb, jglobal + size_t(gwarp) * n * L::LD);
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s) {
     const int i = lane + 32 * s;
@@ -141,11 +136,13 @@ __global__ void __launch_bounds__(kReactThreads) react_kernel(const DevMech m, c
   const int nx = a.hi[0] - a.lo[0] + 1, ny = a.hi[1] - a.lo[1] + 1;
   const int64_t ncells = a.ncells;
 
+#pragma unroll 1
   for (;;) {
     unsigned long long c0 = 0;
     if (lane == 0) c0 = atomicAdd(counter, (unsigned long long)kCellsPerGrab);
     c0 = __shfl_sync(kFull, c0, 0);
     if (int64_t(c0) >= ncells) break;
+#pragma unroll 1
     for (int cc = 0; cc < kCellsPerGrab; ++cc) {
       const int64_t c = int64_t(c0) + cc;
       if (c >= ncells) break;
@@ -176,11 +173,16 @@ __global__ void __launch_bounds__(kReactThreads) react_kernel(const DevMech m, c
       double ry0[NSLOT], y[NSLOT];
       double Tin = a.T.p[oT];
       const double rhoe_init = a.rE.p[oE], rhoesrc = a.rEsrc.p[oEs];
+      __syncwarp();
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) {
         const int k = lane + 32 * s;
         ry0[s] = (k < ns) ? a.rY.p[oY + int64_t(k) * sY] : 0.0;
-        bdf.src[s] = (k < ns) ? a.rYsrc.p[oS + int64_t(k) * sS] : 0.0;
+        wb[L::SRC + k] = (k < ns) ? a.rYsrc.p[oS + int64_t(k) * sS] : 0.0;
+      }
+      if (lane == 0) {
+        wb[L::SM + 24] = rhoe_init;
+        wb[L::SM + 25] = rhoesrc;
       }
       const bool clean = (INTEG == kIntegCvode) && o.clean_init_massfrac && !a.flat;
       double rho_old = 0.0, rho_oldclipped = 0.0, clipped[NSLOT];
@@ -204,25 +206,24 @@ __global__ void __launch_bounds__(kReactThreads) react_kernel(const DevMech m, c
         const double rho = warp_sum(part);
         rho_oldclipped = rho;
         const double rho_inv = 1.0 / rho;
-        double Yw[NSLOT], hrt[NSLOT], cpr[NSLOT], cp;
+        double Yw[NSLOT], cp;
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) Yw[s] = (lane + 32 * s < ns) ? (y[s] * rho_inv) * m.imw[lane + 32 * s] : 0.0;
-        T0 = get_T_given_hY<NSLOT>(m, lane, rhoe_init * rho_inv, Yw, Tin, hrt, cpr, cp);
+        for (int s = 0; s < NSLOT; ++s) Yw[s] = (lane + 32 * s < ns) ? (y[s] * rho_inv) * ldg(m.imw + lane + 32 * s) : 0.0;
+        T0 = get_T_given_hY<L>(rhoe_init * rho_inv, Yw, Tin, cp);
       }
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         if (lane + 32 * s == ns) y[s] = T0;
+      __syncwarp();
 
       CellStats st{};
       int fc;
       if (INTEG == kIntegCvode) {
-        bdf.rhoe_init = rhoe_init;
-        bdf.rhoesrc = rhoesrc;
         bdf.integrate(y, a.time, a.time + a.dt, st);
         fc = st.nfe;
       } else {
         int nfe = 0;
-        fc = rk64_warp<NSLOT>(m, wm, lane, o, y, bdf.src, rhoe_init, rhoesrc, a.time, a.dt, nfe);
+        fc = rk64_warp<L>(wb, lane, o, y, a.time, a.dt, nfe);
         st.nst = fc;
         st.nfe = nfe;
       }
@@ -239,14 +240,14 @@ __global__ void __launch_bounds__(kReactThreads) react_kernel(const DevMech m, c
       for (int s = 0; s < NSLOT; ++s)
         if (lane + 32 * s == ns) Tout = y[s];
       Tout = __shfl_sync(kFull, Tout, ns & 31);
-      const double rE_new = rhoe_init + a.dt * rhoesrc;
+      const double rE_new = __dadd_rn(rhoe_init, __dmul_rn(a.dt, rhoesrc));  // unfused, as the host compiler evaluates ReactorUtils.H:180
       if (!a.flat) {
         const double rho = warp_sum(p2);
         const double rho_inv = 1.0 / rho;
-        double Yw[NSLOT], hrt[NSLOT], cpr[NSLOT], cp;
+        double Yw[NSLOT], cp;
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) Yw[s] = (lane + 32 * s < ns) ? (outv[s] * rho_inv) * m.imw[lane + 32 * s] : 0.0;
-        Tout = get_T_given_hY<NSLOT>(m, lane, rE_new * rho_inv, Yw, Tout, hrt, cpr, cp);
+        for (int s = 0; s < NSLOT; ++s) Yw[s] = (lane + 32 * s < ns) ? (outv[s] * rho_inv) * ldg(m.imw + lane + 32 * s) : 0.0;
+        Tout = get_T_given_hY<L>(rE_new * rho_inv, Yw, Tout, cp);
       }
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) {
@@ -278,55 +279,56 @@ __global__ void __launch_bounds__(kReactThreads) react_kernel(const DevMech m, c
   }
 }
 
-template <int NSLOT>
-__global__ void __launch_bounds__(kReactThreads) rhs_kernel(const DevMech m, int ncells, double t,
+template <class L>
+__global__ void __launch_bounds__(kReactThreads) rhs_kernel(const DevMech* __restrict__ dm, int ncells, double t,
                                                             const double* __restrict__ y,
                                                             const double* __restrict__ rhoe,
                                                             const double* __restrict__ rhoesrc,
-                                                            const double* __restrict__ rYsrc, double* __restrict__ ydot,
-                                                            int ld)
+                                                            const double* __restrict__ rYsrc, double* __restrict__ ydot)
 {
-  extern __shared__ double smem[];
+  constexpr int NSLOT = L::NSLOT, ns = L::NS, n = L::N;
+  double* wb = block_prologue<L>(dm);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t wdoubles = warp_mem_doubles(m.n, m.nsp_pad, m.nr_pad, 0, ld, true);
-  const WarpMem wm = carve(smem + warp * wdoubles, m, 0, ld, nullptr);
-  init_pads(m, wm, lane);
   const int nw = gridDim.x * (blockDim.x >> 5);
   for (int c = blockIdx.x * (blockDim.x >> 5) + warp; c < ncells; c += nw) {
-    double yv[NSLOT], src[NSLOT], yd[NSLOT];
+    __syncwarp();
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       const int i = lane + 32 * s;
-      yv[s] = (i < m.n) ? y[size_t(c) * m.n + i] : 0.0;
-      src[s] = (i < m.ns) ? rYsrc[size_t(c) * m.ns + i] : 0.0;
+      wb[L::YB + i] = (i < n) ? y[size_t(c) * n + i] : 0.0;
+      wb[L::SRC + i] = (i < ns) ? rYsrc[size_t(c) * ns + i] : 0.0;
     }
-    rhs_warp<NSLOT>(m, wm, lane, t, yv, src, rhoe[c], rhoesrc[c], yd);
+    if (lane == 0) {
+      wb[L::SM + 24] = rhoe[c];
+      wb[L::SM + 25] = rhoesrc[c];
+    }
+    __syncwarp();
+    rhs_warp<L>(t);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s)
-      if (lane + 32 * s < m.n) ydot[size_t(c) * m.n + lane + 32 * s] = yd[s];
+      if (lane + 32 * s < n) ydot[size_t(c) * n + lane + 32 * s] = wb[L::FB + lane + 32 * s];
   }
 }
 
-template <int NSLOT>
-__global__ void __launch_bounds__(kReactThreads) jac_kernel(const DevMech m, int ncells, const double* __restrict__ y,
-                                                            double* __restrict__ Jout, int ld)
+template <class L>
+__global__ void __launch_bounds__(kReactThreads) jac_kernel(const DevMech* __restrict__ dm, int ncells,
+                                                            const double* __restrict__ y, double* __restrict__ Jout)
 {
-  extern __shared__ double smem[];
+  constexpr int NSLOT = L::NSLOT, n = L::N, ld = L::LD;
+  double* wb = block_prologue<L>(dm);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t wdoubles = warp_mem_doubles(m.n, m.nsp_pad, m.nr_pad, 0, ld, true);
-  const WarpMem wm = carve(smem + warp * wdoubles, m, 0, ld, nullptr);
-  init_pads(m, wm, lane);
   const int nw = gridDim.x * (blockDim.x >> 5);
-  const int n = m.n;
   for (int c = blockIdx.x * (blockDim.x >> 5) + warp; c < ncells; c += nw) {
-    double yv[NSLOT];
+    __syncwarp();
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) yv[s] = (lane + 32 * s < n) ? y[size_t(c) * n + lane + 32 * s] : 0.0;
-    jac_warp<NSLOT>(m, wm, lane, yv, wm.A);
+    for (int s = 0; s < NSLOT; ++s)
+      wb[L::YB + lane + 32 * s] = (lane + 32 * s < n) ? y[size_t(c) * n + lane + 32 * s] : 0.0;
+    __syncwarp();
+    jac_warp<L>(wb + L::A);
     // column-major output like the SUNDenseMatrix handed to CVODE
     for (int e = lane; e < n * n; e += 32) {
       const int col = e / n, row = e - col * n;
-      Jout[size_t(c) * n * n + e] = wm.A[row * ld + col];
+      Jout[size_t(c) * n * n + e] = wb[L::A + row * ld + col];
     }
     __syncwarp();
   }
@@ -374,91 +376,160 @@ cudaError_t launch_dfma_peak(double* scratch, int blocks, int iters, cudaStream_
 }
 
 // ------------------------------------------------------------------------------------------------
-// launchers
+// launchers: dispatch on (mechanism, order class, integrator)
 // ------------------------------------------------------------------------------------------------
-static int nslot_of(const DevMech& m) { return (m.n + 31) / 32; }
+using LLi2 = Lay<9, 21, 2>;    using LLi5 = Lay<9, 21, 5>;    using LLi0 = Lay<9, 21, 0>;
+using LDr2 = Lay<21, 84, 2>;   using LDr5 = Lay<21, 84, 5>;   using LDr0 = Lay<21, 84, 0>;
+using LDo2 = Lay<53, 268, 2>;  using LDo5 = Lay<53, 268, 5>;  using LDo0 = Lay<53, 268, 0>;
 
-int ld_for(const DevMech& m) { return (m.n % 2 == 0) ? m.n + 1 : m.n; }
-
-size_t react_smem_bytes(const DevMech& m, int qmax, bool j_in_smem, int warps_per_block)
+// calls F.template run<Lay, INTEG>() for the matching instantiation
+template <class F>
+static cudaError_t dispatch(const DevMech& m, int integ, int qmax, F&& f)
 {
-  return warp_mem_doubles(m.n, m.nsp_pad, m.nr_pad, qmax, ld_for(m), j_in_smem) * sizeof(double) * warps_per_block;
-}
-
-template <int NSLOT, int INTEG>
-static cudaError_t launch_react_t(const DevMech& m, const ReactOpts& o, const BoxArgs& a, const LaunchCfg& cfg,
-                                  unsigned long long* counter, unsigned long long* gstats, int* status,
-                                  double* jglobal, cudaStream_t stream)
-{
-  auto kern = react_kernel<NSLOT, INTEG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.smem_bytes));
-  if (e != cudaSuccess) return e;
-  kern<<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(m, o, a, counter, gstats, status, jglobal);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a, const LaunchCfg& cfg, int integ,
-                         unsigned long long* counter, unsigned long long* gstats, int* status, double* jglobal,
-                         cudaStream_t stream)
-{
-  const int ns = nslot_of(m);
-  if (ns == 1 && integ == kIntegCvode) return launch_react_t<1, kIntegCvode>(m, o, a, cfg, counter, gstats, status, jglobal, stream);
-  if (ns == 1 && integ == kIntegRK64) return launch_react_t<1, kIntegRK64>(m, o, a, cfg, counter, gstats, status, jglobal, stream);
-  if (ns == 2 && integ == kIntegCvode) return launch_react_t<2, kIntegCvode>(m, o, a, cfg, counter, gstats, status, jglobal, stream);
-  if (ns == 2 && integ == kIntegRK64) return launch_react_t<2, kIntegRK64>(m, o, a, cfg, counter, gstats, status, jglobal, stream);
+  const int qc = (integ == kIntegRK64) ? 0 : (qmax <= 2 ? 2 : 5);
+#define PLM_CASE(NS, NR, L0, L2, L5)                                                       \
+  if (m.ns == NS && m.nr == NR) {                                                          \
+    if (qc == 0) return f.template run<L0, kIntegRK64>();                                  \
+    if (qc == 2) return f.template run<L2, kIntegCvode>();                                 \
+    return f.template run<L5, kIntegCvode>();                                              \
+  }
+  PLM_CASE(9, 21, LLi0, LLi2, LLi5)
+  PLM_CASE(21, 84, LDr0, LDr2, LDr5)
+  PLM_CASE(53, 268, LDo0, LDo2, LDo5)
+#undef PLM_CASE
   return cudaErrorInvalidValue;
 }
 
-int react_occupancy(const DevMech& m, int integ, int threads, size_t smem)
+struct SmemQuery {
+  int wpb;
+  size_t* out;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    *out = (size_t(kHdr) + size_t(wpb) * L::TOTAL) * sizeof(double);
+    return cudaSuccess;
+  }
+};
+size_t react_smem_bytes(const DevMech& m, int integ, int qmax, int warps_per_block)
+{
+  size_t v = 0;
+  SmemQuery q{warps_per_block, &v};
+  dispatch(m, integ, qmax, q);
+  return v;
+}
+
+struct JQuery {
+  size_t* out;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    *out = size_t(L::N) * L::LD;
+    return cudaSuccess;
+  }
+};
+size_t react_jsave_doubles(const DevMech& m)
+{
+  size_t v = 0;
+  JQuery q{&v};
+  dispatch(m, kIntegCvode, 2, q);
+  return v;
+}
+
+struct OccQuery {
+  int threads;
+  size_t smem;
+  int* nb;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    auto k = react_kernel<L, IG>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, threads, smem);
+  }
+};
+int react_occupancy(const DevMech& m, int integ, int qmax, int threads, size_t smem)
 {
   int nb = 0;
-  const int ns = nslot_of(m);
-  cudaError_t e = cudaErrorInvalidValue;
-#define PLM_OCC(NS, IG)                                                                                         \
-  {                                                                                                             \
-    auto k = react_kernel<NS, IG>;                                                                              \
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));                            \
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem);                                   \
-  }
-  if (ns == 1 && integ == kIntegCvode) PLM_OCC(1, kIntegCvode)
-  else if (ns == 1) PLM_OCC(1, kIntegRK64)
-  else if (integ == kIntegCvode) PLM_OCC(2, kIntegCvode)
-  else PLM_OCC(2, kIntegRK64)
-#undef PLM_OCC
-  return e == cudaSuccess ? nb : -1;
+  OccQuery q{threads, smem, &nb};
+  return dispatch(m, integ, qmax, q) == cudaSuccess ? nb : -1;
 }
 
-cudaError_t launch_rhs(const DevMech& m, int ncells, double t, const double* y, const double* rhoe,
+struct ReactLaunch {
+  const DevMech* dm;
+  const ReactOpts& o;
+  const BoxArgs& a;
+  const LaunchCfg& cfg;
+  unsigned long long *counter, *gstats;
+  int* status;
+  double* jglobal;
+  cudaStream_t stream;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    auto kern = react_kernel<L, IG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.smem_bytes));
+    if (e != cudaSuccess) return e;
+    kern<<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(dm, o, a, counter, gstats, status, jglobal);
+    return cudaGetLastError();
+  }
+};
+cudaError_t launch_react(const DevMech& m, const DevMech* dm, const ReactOpts& o, const BoxArgs& a, const LaunchCfg& cfg,
+                         int integ, unsigned long long* counter, unsigned long long* gstats, int* status,
+                         double* jglobal, cudaStream_t stream)
+{
+  ReactLaunch l{dm, o, a, cfg, counter, gstats, status, jglobal, stream};
+  return dispatch(m, integ, o.qmax, l);
+}
+
+struct RhsLaunch {
+  const DevMech* dm;
+  int ncells;
+  double t;
+  const double *y, *rhoe, *rhoesrc, *rYsrc;
+  double* ydot;
+  cudaStream_t stream;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    const int wpb = kReactThreads / 32;
+    const size_t smem = (size_t(kHdr) + size_t(wpb) * L::TOTAL) * sizeof(double);
+    const int blocks = std::max(1, std::min((ncells + wpb - 1) / wpb, 148 * 4));
+    cudaError_t e = cudaFuncSetAttribute(rhs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    rhs_kernel<L><<<blocks, kReactThreads, smem, stream>>>(dm, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot);
+    return cudaGetLastError();
+  }
+};
+cudaError_t launch_rhs(const DevMech& m, const DevMech* dm, int ncells, double t, const double* y, const double* rhoe,
                        const double* rhoesrc, const double* rYsrc, double* ydot, cudaStream_t stream)
 {
-  const int ld = ld_for(m);
-  const int wpb = 4;
-  const size_t smem = warp_mem_doubles(m.n, m.nsp_pad, m.nr_pad, 0, ld, true) * sizeof(double) * wpb;
-  const int blocks = std::max(1, std::min((ncells + wpb - 1) / wpb, 148 * 8));
-  if (nslot_of(m) == 1) {
-    cudaFuncSetAttribute(rhs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    rhs_kernel<1><<<blocks, wpb * 32, smem, stream>>>(m, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot, ld);
-  } else {
-    cudaFuncSetAttribute(rhs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    rhs_kernel<2><<<blocks, wpb * 32, smem, stream>>>(m, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot, ld);
-  }
-  return cudaGetLastError();
+  RhsLaunch l{dm, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot, stream};
+  return dispatch(m, kIntegCvode, 2, l);
 }
 
-cudaError_t launch_jac(const DevMech& m, int ncells, const double* y, double* J, cudaStream_t stream)
-{
-  const int ld = ld_for(m);
-  const int wpb = 2;
-  const size_t smem = warp_mem_doubles(m.n, m.nsp_pad, m.nr_pad, 0, ld, true) * sizeof(double) * wpb;
-  const int blocks = std::max(1, std::min((ncells + wpb - 1) / wpb, 148 * 8));
-  if (nslot_of(m) == 1) {
-    cudaFuncSetAttribute(jac_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    jac_kernel<1><<<blocks, wpb * 32, smem, stream>>>(m, ncells, y, J, ld);
-  } else {
-    cudaFuncSetAttribute(jac_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    jac_kernel<2><<<blocks, wpb * 32, smem, stream>>>(m, ncells, y, J, ld);
+struct JacLaunch {
+  const DevMech* dm;
+  int ncells;
+  const double* y;
+  double* J;
+  cudaStream_t stream;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    const int wpb = kReactThreads / 32;
+    const size_t smem = (size_t(kHdr) + size_t(wpb) * L::TOTAL) * sizeof(double);
+    const int blocks = std::max(1, std::min((ncells + wpb - 1) / wpb, 148 * 4));
+    cudaError_t e = cudaFuncSetAttribute(jac_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    jac_kernel<L><<<blocks, kReactThreads, smem, stream>>>(dm, ncells, y, J);
+    return cudaGetLastError();
   }
-  return cudaGetLastError();
+};
+cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const double* y, double* J, cudaStream_t stream)
+{
+  JacLaunch l{dm, ncells, y, J, stream};
+  return dispatch(m, kIntegCvode, 2, l);
 }
 
 cudaError_t launch_box_costs(const double* FC, const int64_t* off, int nboxes, long long* costs, cudaStream_t stream)

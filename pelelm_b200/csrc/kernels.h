@@ -26,7 +26,6 @@ struct BoxArgs {
   int lo[3], hi[3];
   int64_t ncells;
   int flat;    // 1: AoS flat API (rY [c][n] incl. T, rYsrc [c][ns], rE/rEsrc/FC [c])
-  int ld;
   plm_a4d rY, rYsrc, T, rE, rEsrc, FC;
   plm_a4i mask;
   double dt, time;
@@ -37,15 +36,16 @@ struct LaunchCfg {
   size_t smem_bytes;
 };
 
-int ld_for(const DevMech& m);
-size_t react_smem_bytes(const DevMech& m, int qmax, bool j_in_smem, int warps_per_block);
-int react_occupancy(const DevMech& m, int integ, int threads, size_t smem);
-cudaError_t launch_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a, const LaunchCfg& cfg, int integ,
-                         unsigned long long* counter, unsigned long long* gstats, int* status, double* jglobal,
-                         cudaStream_t stream);
-cudaError_t launch_rhs(const DevMech& m, int ncells, double t, const double* y, const double* rhoe,
+// m: host copy of the descriptor (dimensions for dispatch); dm: its device copy (what the kernels read)
+size_t react_smem_bytes(const DevMech& m, int integ, int qmax, int warps_per_block);
+size_t react_jsave_doubles(const DevMech& m);
+int react_occupancy(const DevMech& m, int integ, int qmax, int threads, size_t smem);
+cudaError_t launch_react(const DevMech& m, const DevMech* dm, const ReactOpts& o, const BoxArgs& a, const LaunchCfg& cfg,
+                         int integ, unsigned long long* counter, unsigned long long* gstats, int* status,
+                         double* jglobal, cudaStream_t stream);
+cudaError_t launch_rhs(const DevMech& m, const DevMech* dm, int ncells, double t, const double* y, const double* rhoe,
                        const double* rhoesrc, const double* rYsrc, double* ydot, cudaStream_t stream);
-cudaError_t launch_jac(const DevMech& m, int ncells, const double* y, double* J, cudaStream_t stream);
+cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const double* y, double* J, cudaStream_t stream);
 cudaError_t launch_dfma_peak(double* scratch, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_box_costs(const double* FC, const int64_t* off, int nboxes, long long* costs, cudaStream_t stream);
 

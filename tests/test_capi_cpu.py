@@ -102,3 +102,23 @@ def test_knapsack_vs_port(plm_lib, port_lib):
     # heaviest bucket goes to the least-loaded rank; empty weights are legal
     a, _ = capi.knapsack(np.zeros(16, dtype=np.int64), 4)
     assert a.min() >= 0 and a.max() < 4
+
+
+def test_reference_factory_knows_b200_reactors():
+    """The adaptor (pelelm_b200/adaptor) registers with the reference's own factory; without a GPU creation must abort
+    with the library's no-device message (no silent CPU path)."""
+    import subprocess
+    import sys
+    import torch
+    from oracle import pyoracle
+    if not pyoracle.ref_available("LiDryer", b200=True):
+        pytest.skip("oracle/_ref/libref_LiDryer_b200.so not built")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_dropin.py")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from oracle.pyoracle import Ref\n"
+            "Ref('LiDryer', b200=True).init(integrator='ReactorRK64B200')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "Creating ReactorBase instance: ReactorRK64B200" in r.stdout
+    assert "no CUDA device" in r.stderr

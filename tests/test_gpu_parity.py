@@ -52,6 +52,8 @@ def test_react_vs_reference_golden(capi, mech, case):
     small = mech != "dodecane_lu"
     exact_fc = small and case != "cv_dq"
     cmp_rtol = max(1e-6, 100 * ikw.get("rtol", 0.0))
+    if case == "cv_dq":  # the difference-quotient Jacobian amplifies last-bit RHS noise into the Newton iteration
+        cmp_rtol = 1e-5
     check_state(got, ref, atol, tag="%s/%s" % (mech, case), rtol=cmp_rtol, fc_equal_min=0.9 if exact_fc else None,
                 fc_rel=0.05 if small else 0.15)
     assert not status.any()
