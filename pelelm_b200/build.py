@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libplmchem.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("PLM_EXTRA_CUFLAGS", "").split()
 
 SOURCES = ["kernels.cu", "capi.cpp", "dev_tables.cpp", "knapsack.cpp", "gen/tables_LiDryer.c", "gen/tables_drm19.c",
            "gen/tables_dodecane_lu.c"]

@@ -51,8 +51,16 @@ enum { NO_FAILURES = 0, FAIL_BAD_J = 1, FAIL_OTHER = 2 };
 enum { NLS_SUCCESS = 0, NLS_CONV_RECVR = 902 };
 }  // namespace cvc
 
-// SUNRpowerR (sundials_math.c:56): pow(base, e) for base > 0 else 0; exp(e*log(base)) keeps the device code call-free
-__device__ __noinline__ double rpowR(double base, double e) { return base <= 0.0 ? 0.0 : exp(e * log(base)); }
+// SUNRpowerR(base, 1/k) (sundials_math.c:56): pow(base, 1.0/k) for base > 0 else 0. The step-size controller only
+// takes k-th roots with k = L or L+1 (2..7): square and cube roots have dedicated short sequences.
+__device__ __noinline__ double rroot(double base, int k)
+{
+  if (base <= 0.0) return 0.0;
+  if (k == 2) return sqrt(base);
+  if (k == 3) return cbrt(base);
+  if (k == 4) return sqrt(sqrt(base));
+  return dexp(log(base) / double(k));
+}
 __device__ __forceinline__ double rpowI(double base, int e)
 {
   double prod = 1.0;
@@ -156,7 +164,7 @@ __device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::
   for (int s = 0; s < NSLOT; ++s) {
     const double* row = wb + L::A + min(lane + 32 * s, n - 1) * ld;
     double a0 = 0.0, a1 = 0.0;
-#pragma unroll 11
+#pragma unroll 4
     for (int j = 0; j + 1 < n; j += 2) {
       a0 = fma(row[j], pb[j], a0);
       a1 = fma(row[j + 1], pb[j + 1], a1);
@@ -621,7 +629,7 @@ struct BdfWarp {
     if (nef == o.maxnef) return cvc::CV_ERR_FAILURE;
     etamax = 1.0;
     if (nef <= cvc::MXNEF1) {
-      eta = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L_) + cvc::ADDON);
+      eta = 1.0 / (rroot(cvc::BIAS2 * dsm, L_) + cvc::ADDON);
       eta = fmax(cvc::ETA_MIN_EF, eta);
       if (nef >= cvc::SMALL_NEF) eta = fmin(eta, cvc::ETA_MAX_EF);
       rescale();
@@ -696,7 +704,7 @@ struct BdfWarp {
       eta = 1.0;
       return;
     }
-    const double etaq = 1.0 / (rpowR(cvc::BIAS2 * dsm, 1.0 / L_) + cvc::ADDON);
+    const double etaq = 1.0 / (rroot(cvc::BIAS2 * dsm, L_) + cvc::ADDON);
     if (qwait != 0) {
       eta = etaq;
       qprime = q;
@@ -714,7 +722,7 @@ struct BdfWarp {
           a += p * p;
         }
       const double ddn = sqrt(warp_sum(a) / n) * tq[1];
-      etaqm1 = 1.0 / (rpowR(cvc::BIAS1 * ddn, 1.0 / q) + cvc::ADDON);
+      etaqm1 = 1.0 / (rroot(cvc::BIAS1 * ddn, q) + cvc::ADDON);
     }
     if (q != o.qmax && saved_tq5 != 0.0) {
       const double cquot = (tq[5] / saved_tq5) * rpowI(h / tau[2], L_);
@@ -722,7 +730,7 @@ struct BdfWarp {
       for (int s = 0; s < NSLOT; ++s)
         tv[s] = valid(s) ? -cquot * wb[L::ZN + o.qmax * NP + lane + 32 * s] + acor[s] : 0.0;
       const double dup = wrms(tv, ewt) * tq[3];
-      etaqp1 = 1.0 / (rpowR(cvc::BIAS3 * dup, 1.0 / (L_ + 1)) + cvc::ADDON);
+      etaqp1 = 1.0 / (rroot(cvc::BIAS3 * dup, L_ + 1) + cvc::ADDON);
     }
     const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
     if ((etam > cvc::ETA_MIN_FX) && (etam < cvc::ETA_MAX_FX)) {

@@ -73,10 +73,10 @@ __device__ __forceinline__ int rk64_warp(double* wb, int lane, const ReactOpts& 
     // NaN-propagating max is not needed: the reference's comparison chain also drops NaNs
     const double max_err = warp_max(me);
     if (max_err < o.atol) {
-      const double cf = betaerr * exp(exp1 * log(o.atol / max_err));
+      const double cf = betaerr * dexp(exp1 * log(o.atol / max_err));
       dt_rk = fmin(dt_rk_max, dt_rk * cf);
     } else {
-      const double cf = betaerr * exp(exp2 * log(o.atol / max_err));
+      const double cf = betaerr * dexp(exp2 * log(o.atol / max_err));
       dt_rk = fmax(dt_rk_min, dt_rk * cf);
     }
     dt_rk = fmin(dt_rk, time_out - current_time);
@@ -109,8 +109,11 @@ __device__ __forceinline__ int64_t a4_off(const plm_a4d& a, int i, int j, int k)
   return int64_t(i - a.lo[0]) + int64_t(j - a.lo[1]) * a.jstride + int64_t(k - a.lo[2]) * a.kstride;
 }
 
+#ifndef PLM_MIN_BLOCKS
+#define PLM_MIN_BLOCKS 4
+#endif
 template <class L, int INTEG>
-__global__ void __launch_bounds__(kReactThreads, 4)
+__global__ void __launch_bounds__(kReactThreads, PLM_MIN_BLOCKS)
     react_kernel(const DevMech* __restrict__ dm, const ReactOpts o, const BoxArgs a, unsigned long long* __restrict__ counter,
                  unsigned long long* __restrict__ gstats, int* __restrict__ status, double* __restrict__ jglobal)
 {
