@@ -137,8 +137,21 @@ __device__ __noinline__ int gjinv_warp()
         double* row = A + i * ld;
         const double f = row[k];
         row[k] = 0.0;
+        if (L::PAIRS) {  // rows are 16-byte aligned and an odd number of 16-byte units apart: conflict-free pair sweeps
+          const double2* rk2 = reinterpret_cast<const double2*>(rk);
+          double2* row2 = reinterpret_cast<double2*>(row);
 #pragma unroll 2
-        for (int j = 0; j < n; ++j) row[j] -= rk[j] * f;
+          for (int j = 0; j < n / 2; ++j) {
+            const double2 p = rk2[j];
+            double2 r = row2[j];
+            r.x -= p.x * f;
+            r.y -= p.y * f;
+            row2[j] = r;
+          }
+        } else {
+#pragma unroll 2
+          for (int j = 0; j < n; ++j) row[j] -= rk[j] * f;
+        }
       }
     }
     __syncwarp();
@@ -164,12 +177,23 @@ __device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::
   for (int s = 0; s < NSLOT; ++s) {
     const double* row = wb + L::A + min(lane + 32 * s, n - 1) * ld;
     double a0 = 0.0, a1 = 0.0;
+    if (L::PAIRS) {
+      const double2* row2 = reinterpret_cast<const double2*>(row);
+      const double2* pb2 = reinterpret_cast<const double2*>(pb);
 #pragma unroll 4
-    for (int j = 0; j + 1 < n; j += 2) {
-      a0 = fma(row[j], pb[j], a0);
-      a1 = fma(row[j + 1], pb[j + 1], a1);
+      for (int j = 0; j < n / 2; ++j) {
+        const double2 w = row2[j], b = pb2[j];
+        a0 = fma(w.x, b.x, a0);
+        a1 = fma(w.y, b.y, a1);
+      }
+    } else {
+#pragma unroll 4
+      for (int j = 0; j + 1 < n; j += 2) {
+        a0 = fma(row[j], pb[j], a0);
+        a1 = fma(row[j + 1], pb[j + 1], a1);
+      }
+      if (n & 1) a0 = fma(row[n - 1], pb[n - 1], a0);
     }
-    if (n & 1) a0 = fma(row[n - 1], pb[n - 1], a0);
     x[s] = a0 + a1;
   }
   __syncwarp();
@@ -204,6 +228,12 @@ struct BdfWarp {
     return v;
   }
 
+  // sqrt(sum / n); a zero (or NaN / inf) sum goes through the library routine
+  static __device__ __forceinline__ double wrms_finish(double sum)
+  {
+    const double v = sum * (1.0 / n);
+    return (v > 1e-290 && v < 1e290) ? fsqrt(v) : sqrt(v);
+  }
   __device__ __forceinline__ double wrms(const double (&x)[NSLOT], const double (&w)[NSLOT]) const
   {
     double a = 0.0;
@@ -213,7 +243,7 @@ struct BdfWarp {
         const double p = x[s] * w[s];
         a += p * p;
       }
-    return sqrt(warp_sum(a) / n);
+    return wrms_finish(warp_sum(a));
   }
   __device__ __forceinline__ double wrms_zn(int j) const
   {
@@ -236,7 +266,7 @@ struct BdfWarp {
       if (valid(s)) {
         const double t = o.rtol * fabs(zn(0, s)) + atolv[s];
         if (t <= 0.0) bad = 1;
-        ewt[s] = 1.0 / t;
+        ewt[s] = (t > 1e-290) ? frcp(t) : 1.0 / t;
       }
     }
     return __any_sync(kFull, bad) == 0;
@@ -287,7 +317,7 @@ struct BdfWarp {
   __device__ __forceinline__ int lsetup()
   {
     double* A = wb + L::A;
-    const double dgamma = fabs((gamma / gammap) - 1.0);
+    const double dgamma = fabs(fdiv(gamma, gammap) - 1.0);
     const bool jbad = (nst == 0) || (nst >= nstlj + o.msbj) ||
                       ((convfail == cvc::FAIL_BAD_J) && (dgamma < cvc::DGMAX_JBAD)) || (convfail == cvc::FAIL_OTHER);
     __syncwarp();
@@ -372,15 +402,15 @@ struct BdfWarp {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) dl[s] = valid(s) ? dl[s] : 0.0;
         if (gamrat != 1.0) {
-          const double sc = 2.0 / (1.0 + gamrat);
+          const double sc = fdiv(2.0, 1.0 + gamrat);
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s) dl[s] *= sc;
         }
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) acor[s] = valid(s) ? acor[s] + dl[s] : 0.0;
         const double del = wrms(dl, ewt);
-        if (mit > 0) crate = fmax(cvc::CRDOWN * crate, del / delp);
-        const double dcon = del * fmin(1.0, crate) / tq[4];
+        if (mit > 0) crate = fmax(cvc::CRDOWN * crate, fdiv(del, delp));
+        const double dcon = fdiv(del * fmin(1.0, crate), tq[4]);
         if (dcon <= 1.0) {
           acnrm = (mit == 0) ? del : wrms(acor, ewt);
           return cvc::NLS_SUCCESS;
@@ -548,7 +578,7 @@ struct BdfWarp {
       for (int j = 2; j < QM; j++) {
         if (j < q) {
           hsum += tau[j - 1];
-          xi_inv = h / hsum;
+          xi_inv = fdiv(h, hsum);
           alpha0 -= 1.0 / j;
 #pragma unroll
           for (int i = j; i >= 1; i--) lc[i] += lc[i - 1] * xi_inv;
@@ -557,7 +587,7 @@ struct BdfWarp {
       alpha0 -= 1.0 / q;
       xistar_inv = -lc[1] - alpha0;
       hsum += sel(tau, q - 1);
-      xi_inv = h / hsum;
+      xi_inv = fdiv(h, hsum);
       alpha0_hat = -lc[1] - xi_inv;
 #pragma unroll
       for (int i = QM; i >= 1; i--)
@@ -566,29 +596,29 @@ struct BdfWarp {
     const double lq = sel(lc, q);
     const double A1 = 1.0 - alpha0_hat + alpha0;
     const double A2 = 1.0 + q * A1;
-    tq[2] = fabs(A1 / (alpha0 * A2));
-    tq[5] = fabs(A2 * xistar_inv / (lq * xi_inv));
+    tq[2] = fabs(fdiv(A1, alpha0 * A2));
+    tq[5] = fabs(fdiv(A2 * xistar_inv, lq * xi_inv));
     if (qwait == 1) {
       if (q > 1) {
-        const double C = xistar_inv / lq;
+        const double C = fdiv(xistar_inv, lq);
         const double A3 = alpha0 + 1.0 / q;
         const double A4 = alpha0_hat + xi_inv;
-        const double Cpinv = (1.0 - A4 + A3) / A3;
+        const double Cpinv = fdiv(1.0 - A4 + A3, A3);
         tq[1] = fabs(C * Cpinv);
       } else
         tq[1] = 1.0;
       hsum += sel(tau, q);
-      xi_inv = h / hsum;
+      xi_inv = fdiv(h, hsum);
       const double A5 = alpha0 - (1.0 / (q + 1));
       const double A6 = alpha0_hat - xi_inv;
-      const double Cppinv = (1.0 - A6 + A5) / A2;
-      tq[3] = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+      const double Cppinv = fdiv(1.0 - A6 + A5, A2);
+      tq[3] = fabs(fdiv(Cppinv, xi_inv * (q + 2) * A5));
     }
-    tq[4] = cvc::CORTES / tq[2];
-    rl1 = 1.0 / lc[1];
+    tq[4] = fdiv(cvc::CORTES, tq[2]);
+    rl1 = frcp(lc[1]);
     gamma = h * rl1;
     if (nst == 0) gammap = gamma;
-    gamrat = (nst > 0) ? gamma / gammap : 1.0;
+    gamrat = (nst > 0) ? fdiv(gamma, gammap) : 1.0;
   }
 
   __device__ __forceinline__ int nls(int nflag)
@@ -704,7 +734,7 @@ struct BdfWarp {
       eta = 1.0;
       return;
     }
-    const double etaq = 1.0 / (rroot(cvc::BIAS2 * dsm, L_) + cvc::ADDON);
+    const double etaq = frcp(rroot(cvc::BIAS2 * dsm, L_) + cvc::ADDON);
     if (qwait != 0) {
       eta = etaq;
       qprime = q;
@@ -721,7 +751,7 @@ struct BdfWarp {
           const double p = wb[L::ZN + q * NP + lane + 32 * s] * ewt[s];
           a += p * p;
         }
-      const double ddn = sqrt(warp_sum(a) / n) * tq[1];
+      const double ddn = wrms_finish(warp_sum(a)) * tq[1];
       etaqm1 = 1.0 / (rroot(cvc::BIAS1 * ddn, q) + cvc::ADDON);
     }
     if (q != o.qmax && saved_tq5 != 0.0) {
