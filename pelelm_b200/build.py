@@ -7,7 +7,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libplmchem.so")
+# PLM_VARIANT (development only): build a differently-flagged copy next to the product library, e.g.
+#   PLM_VARIANT=mb6 PLM_EXTRA_CUFLAGS=-DPLM_MIN_BLOCKS=6 python -m pelelm_b200.build ; PLM_LIBPATH=... python bench.py
+VARIANT = os.environ.get("PLM_VARIANT", "")
+LIB = os.path.join(HERE, "libplmchem%s.so" % (("_" + VARIANT) if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("PLM_EXTRA_CUFLAGS", "").split()
@@ -21,7 +24,7 @@ def _newer(src: str, dst: str) -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build" + (("_" + VARIANT) if VARIANT else ""))
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers += [os.path.join(CSRC, "gen", "mech_tables.h"), os.path.join(os.path.dirname(HERE), "include", "plm_chem.h")]

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libplmchem.so")
+LIBPATH = os.environ.get("PLM_LIBPATH") or os.path.join(HERE, "libplmchem.so")  # PLM_LIBPATH: development variants
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
