@@ -272,6 +272,18 @@ def run_gpu_arm(a):
     for bx in boxes.values():
         to_device(bx)
     torch.cuda.synchronize()
+    FCall = FCoff = None
+
+    def bind_fc():
+        """FC of all local boxes as views of one contiguous array, so that the per-box cost reduction is one launch."""
+        nonlocal FCall, FCoff
+        ids = sorted(boxes)
+        FCall = torch.zeros(len(ids) * box_cells, dtype=torch.float64, device=dev)
+        for i, b in enumerate(ids):
+            boxes[b]["FC"] = FCall[i * box_cells:(i + 1) * box_cells]
+        FCoff = torch.arange(0, (len(ids) + 1) * box_cells, box_cells, dtype=torch.int64, device=dev)
+
+    bind_fc()
 
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
     main = torch.cuda.current_stream()
@@ -296,11 +308,9 @@ def run_gpu_arm(a):
                 bx["S"].copy_(bx["S0"], non_blocking=True)
                 react_box(bx, s)
         st = R.stats()  # waits for every launch
-        costs = np.array([int(boxes[b]["FC"].sum().item()) for b in ids], dtype=np.int64) if N == 1 else None
-        if N > 1:
-            FCall = torch.cat([boxes[b]["FC"] for b in ids])
-            off = torch.arange(0, (len(ids) + 1) * box_cells, box_cells, dtype=torch.int64, device=dev)
-            costs = capi.box_costs(FCall, off).cpu().numpy()
+        # per-box cost = sum of FC (PeleLM::getFuncCountDM): one launch of the library's reduction kernel over all local boxes
+        costs = capi.box_costs(FCall, FCoff).cpu().numpy()
+        launches[0] += 1
         full = pd.gather_box_costs(costs, owner)
         new_owner, eff = pd.func_count_dm(full, N, default_owner=owner)
         return pd.reduce_stats(st), full, new_owner, eff
@@ -326,6 +336,7 @@ def run_gpu_arm(a):
             owner = new_owner.copy()
             for bx in boxes.values():
                 to_device(bx)
+            bind_fc()
             torch.cuda.synchronize()
 
     # ---- timed region
@@ -350,9 +361,7 @@ def run_gpu_arm(a):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    n_launch = launches[0] * N  # every rank launches one integration kernel per local box per step (+ box_costs when N>1)
-    if N > 1:
-        n_launch += a.steps * N
+    n_launch = launches[0] * N  # every rank: one integration kernel per local box per step + one box-cost reduction per step
     value = cells_total * a.steps / (ms * 1e-3)
     flops = roofline.algorithmic_flops(a.mech, a.integrator, tot)
     achieved = flops / (ms * 1e-3) * 1e-12 / N  # per GPU

@@ -59,7 +59,19 @@ __device__ __noinline__ double rroot(double base, int k)
   if (k == 2) return sqrt(base);
   if (k == 3) return cbrt(base);
   if (k == 4) return sqrt(sqrt(base));
-  return dexp(log(base) / double(k));
+  return dexp(dlog(base) / double(k));
+}
+// 1.0 / k for the small integers the BDF coefficient formulas divide by (k = 1..7), correctly rounded constants
+__device__ __forceinline__ double inv_int(int k)
+{
+  double v = 1.0;
+  v = (k == 2) ? 0.5 : v;
+  v = (k == 3) ? 1.0 / 3.0 : v;
+  v = (k == 4) ? 0.25 : v;
+  v = (k == 5) ? 0.2 : v;
+  v = (k == 6) ? 1.0 / 6.0 : v;
+  v = (k == 7) ? 1.0 / 7.0 : v;
+  return v;
 }
 __device__ __forceinline__ double rpowI(double base, int e)
 {
@@ -199,23 +211,49 @@ __device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::
   __syncwarp();
 }
 
+// Integrator state of the warp's cell. Everything that lives longer than one statement sits in the warp's shared-memory
+// area (scalars: every lane holds the same bits and stores the same value; per-lane vectors: lane-indexed), reached
+// through references, so that only a handful of registers are live across the right-hand-side call. The first version
+// kept it all in registers: ~90 live values across a call into a function that needs ~120 registers itself, i.e. spills
+// around every call at 128 registers per thread and no way to run more than 16 warps per SM.
 template <class L>
 struct BdfWarp {
   static constexpr int NSLOT = L::NSLOT, n = L::N, NP = L::NP, QM = L::QM, ld = L::LD;
+  static_assert(QM + 1 <= 6, "scalar area holds 6 entries per coefficient array");
+  enum { SC_TAU = 0, SC_TQ = 8, SC_LC = 16, SC_RHOE = 24, SC_RHOESRC = 25, SC_D = 26, SC_I = 40 };
+  struct LaneVec {  // per-lane vector in shared memory: component lane + 32*s
+    double* p;
+    __device__ __forceinline__ double& operator[](int s) const { return p[32 * s]; }
+  };
   const BdfOpts& o;
   const int lane;
   double* const wb;
   double* const Jsave;  // [n*ld] per-warp global scratch
-  double atolv[NSLOT];
-  double ewt[NSLOT], acor[NSLOT], yv[NSLOT], ft[NSLOT], dl[NSLOT], tv[NSLOT];
-  double tau[QM + 1], lc[QM + 1], tq[6];
-  double tn, h, hprime, hscale, eta, etamax;
-  int q, qprime, L_, qwait, indx_acor;
-  double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
-  int nst, nfe, ncfn, netf, nni, nsetups, nje, nstlp, nstlj;
-  int jcur, convfail;
+  const LaneVec atolv, ewt, acor;
+  double yv[NSLOT], ft[NSLOT], dl[NSLOT], tv[NSLOT];  // short-lived temporaries
+  double (&tau)[6], (&lc)[6], (&tq)[6];
+  double &tn, &h, &hprime, &hscale, &eta, &etamax;
+  double &rl1, &gamma, &gammap, &gamrat, &crate, &delp, &acnrm, &saved_tq5;
+  int &q, &qprime, &L_, &qwait, &indx_acor;
+  int &nst, &nfe, &ncfn, &netf, &nni, &nsetups, &nje, &nstlp, &nstlj;
+  int &jcur, &convfail;
 
-  __device__ BdfWarp(const BdfOpts& o_, int lane_, double* wb_, double* js) : o(o_), lane(lane_), wb(wb_), Jsave(js) {}
+  __device__ __forceinline__ double* sc() const { return wb + L::SM; }
+  __device__ __forceinline__ int* si() const { return reinterpret_cast<int*>(wb + L::SM + SC_I); }
+  __device__ BdfWarp(const BdfOpts& o_, int lane_, double* wb_, double* js)
+      : o(o_), lane(lane_), wb(wb_), Jsave(js),
+        atolv{wb_ + L::ATOL + lane_}, ewt{wb_ + L::EWT + lane_}, acor{wb_ + L::ACOR + lane_},
+        tau(*reinterpret_cast<double(*)[6]>(wb_ + L::SM + SC_TAU)), lc(*reinterpret_cast<double(*)[6]>(wb_ + L::SM + SC_LC)),
+        tq(*reinterpret_cast<double(*)[6]>(wb_ + L::SM + SC_TQ)),
+        tn(sc()[SC_D + 0]), h(sc()[SC_D + 1]), hprime(sc()[SC_D + 2]), hscale(sc()[SC_D + 3]), eta(sc()[SC_D + 4]),
+        etamax(sc()[SC_D + 5]), rl1(sc()[SC_D + 6]), gamma(sc()[SC_D + 7]), gammap(sc()[SC_D + 8]),
+        gamrat(sc()[SC_D + 9]), crate(sc()[SC_D + 10]), delp(sc()[SC_D + 11]), acnrm(sc()[SC_D + 12]),
+        saved_tq5(sc()[SC_D + 13]),
+        q(si()[0]), qprime(si()[1]), L_(si()[2]), qwait(si()[3]), indx_acor(si()[4]), nst(si()[5]), nfe(si()[6]),
+        ncfn(si()[7]), netf(si()[8]), nni(si()[9]), nsetups(si()[10]), nje(si()[11]), nstlp(si()[12]), nstlj(si()[13]),
+        jcur(si()[14]), convfail(si()[15])
+  {
+  }
 
   __device__ __forceinline__ bool valid(int s) const { return lane + 32 * s < n; }
   __device__ __forceinline__ double& zn(int j, int s) const { return wb[L::ZN + j * NP + lane + 32 * s]; }
@@ -228,13 +266,14 @@ struct BdfWarp {
     return v;
   }
 
-  // sqrt(sum / n); a zero (or NaN / inf) sum goes through the library routine
-  static __device__ __forceinline__ double wrms_finish(double sum)
+  // sqrt(sum / n); a zero (or NaN / inf) sum goes through the library routine. One copy (instruction-cache footprint).
+  static __device__ __noinline__ double wrms_finish(double sum)
   {
     const double v = sum * (1.0 / n);
     return (v > 1e-290 && v < 1e290) ? fsqrt(v) : sqrt(v);
   }
-  __device__ __forceinline__ double wrms(const double (&x)[NSLOT], const double (&w)[NSLOT]) const
+  template <class X, class W>
+  __device__ __forceinline__ double wrms(const X& x, const W& w) const
   {
     double a = 0.0;
 #pragma unroll
@@ -245,16 +284,17 @@ struct BdfWarp {
       }
     return wrms_finish(warp_sum(a));
   }
-  __device__ __forceinline__ double wrms_zn(int j) const
+  // sum_i (zn[0]_i * ewt_i)^2 ; the caller compares it with n / uround^2 (cvode.c:1316-1321: uround * wrms > 1)
+  __device__ __forceinline__ double wss_zn0() const
   {
     double a = 0.0;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s)
       if (valid(s)) {
-        const double p = zn(j, s) * ewt[s];
+        const double p = zn(0, s) * ewt[s];
         a += p * p;
       }
-    return sqrt(warp_sum(a) / n);
+    return warp_sum(a);
   }
   // cvEwtSetSV on zn[0]; false if a weight is non-positive
   __device__ __forceinline__ bool ewtset()
@@ -565,62 +605,73 @@ struct BdfWarp {
     tn = saved_t;
     pascal<-1>();
   }
+  // cvSetBDF + cvSetTqBDF (coefficients formed in registers, stored once). Reusing the previous step's values when
+  // (q, h, tau, qwait == 1) are unchanged was tried and measured slower (the key compare costs more than it saves).
   __device__ __forceinline__ void set_bdf()
   {
-    double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
-    lc[0] = lc[1] = xi_inv = xistar_inv = 1.0;
+    const int q_ = q;
+    const double h_ = h;
+    const bool qw1 = (qwait == 1);
+    {
+      double l[QM + 1];
+      double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
+      l[0] = l[1] = xi_inv = xistar_inv = 1.0;
 #pragma unroll
-    for (int i = 2; i <= QM; i++) lc[i] = 0.0;
-    alpha0 = alpha0_hat = -1.0;
-    hsum = h;
-    if (q > 1) {
+      for (int i = 2; i <= QM; i++) l[i] = 0.0;
+      alpha0 = alpha0_hat = -1.0;
+      hsum = h_;
+      if (q_ > 1) {
 #pragma unroll
-      for (int j = 2; j < QM; j++) {
-        if (j < q) {
-          hsum += tau[j - 1];
-          xi_inv = fdiv(h, hsum);
-          alpha0 -= 1.0 / j;
+        for (int j = 2; j < QM; j++) {
+          if (j < q_) {
+            hsum += tau[j - 1];
+            xi_inv = fdiv(h_, hsum);
+            alpha0 -= 1.0 / j;
 #pragma unroll
-          for (int i = j; i >= 1; i--) lc[i] += lc[i - 1] * xi_inv;
+            for (int i = j; i >= 1; i--) l[i] += l[i - 1] * xi_inv;
+          }
         }
-      }
-      alpha0 -= 1.0 / q;
-      xistar_inv = -lc[1] - alpha0;
-      hsum += sel(tau, q - 1);
-      xi_inv = fdiv(h, hsum);
-      alpha0_hat = -lc[1] - xi_inv;
+        alpha0 -= inv_int(q_);
+        xistar_inv = -l[1] - alpha0;
+        hsum += tau[q_ - 1];
+        xi_inv = fdiv(h_, hsum);
+        alpha0_hat = -l[1] - xi_inv;
 #pragma unroll
-      for (int i = QM; i >= 1; i--)
-        if (i <= q) lc[i] += lc[i - 1] * xistar_inv;
+        for (int i = QM; i >= 1; i--)
+          if (i <= q_) l[i] += l[i - 1] * xistar_inv;
+      }
+      const double lq = sel(l, q_);
+      const double A1 = 1.0 - alpha0_hat + alpha0;
+      const double A2 = 1.0 + q_ * A1;
+      const double tq2 = fabs(fdiv(A1, alpha0 * A2));
+      tq[2] = tq2;
+      tq[5] = fabs(fdiv(A2 * xistar_inv, lq * xi_inv));
+      if (qw1) {
+        if (q_ > 1) {
+          const double C = fdiv(xistar_inv, lq);
+          const double A3 = alpha0 + inv_int(q_);
+          const double A4 = alpha0_hat + xi_inv;
+          const double Cpinv = fdiv(1.0 - A4 + A3, A3);
+          tq[1] = fabs(C * Cpinv);
+        } else
+          tq[1] = 1.0;
+        hsum += tau[q_];
+        xi_inv = fdiv(h_, hsum);
+        const double A5 = alpha0 - inv_int(q_ + 1);
+        const double A6 = alpha0_hat - xi_inv;
+        const double Cppinv = fdiv(1.0 - A6 + A5, A2);
+        tq[3] = fabs(fdiv(Cppinv, xi_inv * (q_ + 2) * A5));
+      }
+      tq[4] = fdiv(cvc::CORTES, tq2);
+#pragma unroll
+      for (int i = 0; i <= QM; i++) lc[i] = l[i];
+      rl1 = frcp(l[1]);
     }
-    const double lq = sel(lc, q);
-    const double A1 = 1.0 - alpha0_hat + alpha0;
-    const double A2 = 1.0 + q * A1;
-    tq[2] = fabs(fdiv(A1, alpha0 * A2));
-    tq[5] = fabs(fdiv(A2 * xistar_inv, lq * xi_inv));
-    if (qwait == 1) {
-      if (q > 1) {
-        const double C = fdiv(xistar_inv, lq);
-        const double A3 = alpha0 + 1.0 / q;
-        const double A4 = alpha0_hat + xi_inv;
-        const double Cpinv = fdiv(1.0 - A4 + A3, A3);
-        tq[1] = fabs(C * Cpinv);
-      } else
-        tq[1] = 1.0;
-      hsum += sel(tau, q);
-      xi_inv = fdiv(h, hsum);
-      const double A5 = alpha0 - (1.0 / (q + 1));
-      const double A6 = alpha0_hat - xi_inv;
-      const double Cppinv = fdiv(1.0 - A6 + A5, A2);
-      tq[3] = fabs(fdiv(Cppinv, xi_inv * (q + 2) * A5));
-    }
-    tq[4] = fdiv(cvc::CORTES, tq[2]);
-    rl1 = frcp(lc[1]);
-    gamma = h * rl1;
-    if (nst == 0) gammap = gamma;
-    gamrat = (nst > 0) ? fdiv(gamma, gammap) : 1.0;
+    const double g = h_ * rl1;
+    gamma = g;
+    if (nst == 0) gammap = g;
+    gamrat = (nst > 0) ? fdiv(g, gammap) : 1.0;
   }
-
   __device__ __forceinline__ int nls(int nflag)
   {
     convfail = ((nflag == cvc::FIRST_CALL) || (nflag == cvc::PREV_ERR_FAIL)) ? cvc::NO_FAILURES : cvc::FAIL_OTHER;
@@ -738,9 +789,15 @@ struct BdfWarp {
     if (qwait != 0) {
       eta = etaq;
       qprime = q;
-      set_eta();
-      return;
+    } else {
+      choose_order(etaq);
     }
+    set_eta();  // single call site (instruction-cache footprint)
+  }
+
+  // cvPrepareNextStep with qwait == 0: cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
+  __device__ __forceinline__ void choose_order(const double etaq)
+  {
     qwait = 2;
     double etaqm1 = 0.0, etaqp1 = 0.0;
     if (q > 1) {
@@ -752,15 +809,15 @@ struct BdfWarp {
           a += p * p;
         }
       const double ddn = wrms_finish(warp_sum(a)) * tq[1];
-      etaqm1 = 1.0 / (rroot(cvc::BIAS1 * ddn, q) + cvc::ADDON);
+      etaqm1 = frcp(rroot(cvc::BIAS1 * ddn, q) + cvc::ADDON);
     }
     if (q != o.qmax && saved_tq5 != 0.0) {
-      const double cquot = (tq[5] / saved_tq5) * rpowI(h / tau[2], L_);
+      const double cquot = fdiv(tq[5], saved_tq5) * rpowI(fdiv(h, tau[2]), L_);
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         tv[s] = valid(s) ? -cquot * wb[L::ZN + o.qmax * NP + lane + 32 * s] + acor[s] : 0.0;
       const double dup = wrms(tv, ewt) * tq[3];
-      etaqp1 = 1.0 / (rroot(cvc::BIAS3 * dup, L_ + 1) + cvc::ADDON);
+      etaqp1 = frcp(rroot(cvc::BIAS3 * dup, L_ + 1) + cvc::ADDON);
     }
     const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
     if ((etam > cvc::ETA_MIN_FX) && (etam < cvc::ETA_MAX_FX)) {
@@ -779,7 +836,6 @@ struct BdfWarp {
       for (int s = 0; s < NSLOT; ++s)
         if (valid(s)) wb[L::ZN + o.qmax * NP + lane + 32 * s] = acor[s];
     }
-    set_eta();
   }
 
   __device__ __forceinline__ int step()
@@ -924,7 +980,7 @@ struct BdfWarp {
           istate = cvc::CV_TOO_MUCH_WORK;
           break;
         }
-        if (DBL_EPSILON * wrms_zn(0) > 1.0) {
+        if (wss_zn0() > double(n) / (DBL_EPSILON * DBL_EPSILON)) {
           istate = cvc::CV_TOO_MUCH_ACC;
           break;
         }

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -209,9 +210,14 @@ int configure(plm_reactor* r)
 {
   if (r->cfg_qmax == r->opts.qmax) return PLM_OK;
   const plm::DevMech& m = r->mech.h;
-  const int wpb = plm::kReactThreads / 32;
-  const size_t smem = plm::react_smem_bytes(m, r->integ, r->opts.qmax, wpb);
+  const int wpb = plm::react_threads(m, r->integ, r->opts.qmax) / 32;
+  if (wpb <= 0) return fail(PLM_ERR_CUDA, "no kernel for this mechanism");
+  size_t smem = plm::react_smem_bytes(m, r->integ, r->opts.qmax, wpb);
   if (smem == 0 || smem > 227 * 1024) return fail(PLM_ERR_CUDA, "no launch configuration fits in shared memory");
+  if (const char* lim = std::getenv("PLM_OCC_LIMIT")) {  // development: cap resident CTAs per SM by padding shared memory
+    const int k = std::atoi(lim);
+    if (k > 0) smem = std::max(smem, size_t(227 * 1024 / (k + 1) + 1024));
+  }
   const int occ = plm::react_occupancy(m, r->integ, r->opts.qmax, wpb * 32, smem);
   if (occ <= 0) return fail(PLM_ERR_CUDA, "kernel cannot be resident (occupancy query failed)");
   r->cfg.blocks = occ * r->num_sms;  // persistent grid: every resident CTA slot of every SM

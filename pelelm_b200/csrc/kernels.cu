@@ -73,10 +73,10 @@ __device__ __forceinline__ int rk64_warp(double* wb, int lane, const ReactOpts& 
     // NaN-propagating max is not needed: the reference's comparison chain also drops NaNs
     const double max_err = warp_max(me);
     if (max_err < o.atol) {
-      const double cf = betaerr * dexp(exp1 * log(o.atol / max_err));
+      const double cf = betaerr * dexp(exp1 * dlog(o.atol / max_err));
       dt_rk = fmin(dt_rk_max, dt_rk * cf);
     } else {
-      const double cf = betaerr * dexp(exp2 * log(o.atol / max_err));
+      const double cf = betaerr * dexp(exp2 * dlog(o.atol / max_err));
       dt_rk = fmax(dt_rk_min, dt_rk * cf);
     }
     dt_rk = fmin(dt_rk, time_out - current_time);
@@ -109,11 +109,36 @@ __device__ __forceinline__ int64_t a4_off(const plm_a4d& a, int i, int j, int k)
   return int64_t(i - a.lo[0]) + int64_t(j - a.lo[1]) * a.jstride + int64_t(k - a.lo[2]) * a.kstride;
 }
 
-#ifndef PLM_MIN_BLOCKS
-#define PLM_MIN_BLOCKS 4
-#endif
+// where cell c of the call lives in the caller's arrays (FAB layout, or the flat AoS layout of the 1dArray API)
+struct CellAddr {
+  int64_t oY, oS, oT, oE, oEs, oF, sY, sS;
+  int mk;
+};
+template <class L>
+__device__ __noinline__ CellAddr cell_addr(const BoxArgs& a, int64_t c)
+{
+  constexpr int ns = L::NS, n = L::N;
+  CellAddr r;
+  r.mk = 1;
+  if (a.flat) {
+    r.oY = c * n; r.oS = c * ns; r.oT = c * n + ns; r.oE = c; r.oEs = c; r.oF = c; r.sY = 1; r.sS = 1;
+  } else {
+    const int nx = a.hi[0] - a.lo[0] + 1, ny = a.hi[1] - a.lo[1] + 1;
+    const int i = a.lo[0] + int(c % nx), j = a.lo[1] + int((c / nx) % ny), k = a.lo[2] + int(c / (int64_t(nx) * ny));
+    r.oY = a4_off(a.rY, i, j, k); r.sY = a.rY.nstride;
+    r.oS = a4_off(a.rYsrc, i, j, k); r.sS = a.rYsrc.nstride;
+    r.oT = a4_off(a.T, i, j, k);
+    r.oE = a4_off(a.rE, i, j, k);
+    r.oEs = a4_off(a.rEsrc, i, j, k);
+    r.oF = a4_off(a.FC, i, j, k);
+    if (a.mask.p) r.mk = a.mask.p[int64_t(i - a.mask.lo[0]) + int64_t(j - a.mask.lo[1]) * a.mask.jstride +
+                                  int64_t(k - a.mask.lo[2]) * a.mask.kstride];
+  }
+  return r;
+}
+
 template <class L, int INTEG>
-__global__ void __launch_bounds__(kReactThreads, PLM_MIN_BLOCKS)
+__global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
     react_kernel(const DevMech* __restrict__ dm, const ReactOpts o, const BoxArgs a, unsigned long long* __restrict__ counter,
                  unsigned long long* __restrict__ gstats, int* __restrict__ status, double* __restrict__ jglobal)
 {
@@ -133,79 +158,76 @@ __global__ void __launch_bounds__(kReactThreads, PLM_MIN_BLOCKS)
     bdf.atolv[s] = (i < n) ? (o.use_typ ? o.typ_vals[i] * o.atol : o.atol) : 1.0;
   }
 
-  unsigned long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // nst nfe nje nsetups nni ncfn netf nfailed
-  unsigned long long nskipped = 0, ndone = 0;
-  int maxfc = 0, minfc = 0x7fffffff;
-  const int nx = a.hi[0] - a.lo[0] + 1, ny = a.hi[1] - a.lo[1] + 1;
+  // statistics: a few atomics per cell (a cell is millions of instructions) instead of accumulators held in registers
+  // across the integration
   const int64_t ncells = a.ncells;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
 
 #pragma unroll 1
   for (;;) {
+    // kCellsPerGrab consecutive cells per grab (full 32-byte sectors of the state arrays) while plenty remain, single
+    // cells near the end of the queue: cell cost varies 10x, and the tail of the call is set by the last grabs
     unsigned long long c0 = 0;
-    if (lane == 0) c0 = atomicAdd(counter, (unsigned long long)kCellsPerGrab);
+    int grab = kCellsPerGrab;
+    if (lane == 0) {
+      const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(counter);
+      if (int64_t(seen) + int64_t(nwarps) * (2 * kCellsPerGrab) >= ncells) grab = 1;
+      c0 = atomicAdd(counter, (unsigned long long)grab);
+    }
     c0 = __shfl_sync(kFull, c0, 0);
+    grab = __shfl_sync(kFull, grab, 0);
     if (int64_t(c0) >= ncells) break;
 #pragma unroll 1
-    for (int cc = 0; cc < kCellsPerGrab; ++cc) {
+    for (int cc = 0; cc < grab; ++cc) {
       const int64_t c = int64_t(c0) + cc;
       if (c >= ncells) break;
-      // cell -> (i,j,k) or flat index
-      int64_t oY, oS, oT, oE, oEs, oF, sY, sS;
-      int mk = 1;
-      if (a.flat) {
-        oY = c * n; oS = c * ns; oT = c * n + ns; oE = c; oEs = c; oF = c; sY = 1; sS = 1;
-      } else {
-        const int i = a.lo[0] + int(c % nx), j = a.lo[1] + int((c / nx) % ny), k = a.lo[2] + int(c / (int64_t(nx) * ny));
-        oY = a4_off(a.rY, i, j, k); sY = a.rY.nstride;
-        oS = a4_off(a.rYsrc, i, j, k); sS = a.rYsrc.nstride;
-        oT = a4_off(a.T, i, j, k);
-        oE = a4_off(a.rE, i, j, k);
-        oEs = a4_off(a.rEsrc, i, j, k);
-        oF = a4_off(a.FC, i, j, k);
-        if (a.mask.p) mk = a.mask.p[int64_t(i - a.mask.lo[0]) + int64_t(j - a.mask.lo[1]) * a.mask.jstride +
-                                    int64_t(k - a.mask.lo[2]) * a.mask.kstride];
-      }
-      if (INTEG == kIntegCvode && mk == -1) {  // ReactorCvode.cpp:1395, :1439-1441 (RK64 ignores the mask)
+      CellAddr ad = cell_addr<L>(a, c);
+      if (INTEG == kIntegCvode && ad.mk == -1) {  // ReactorCvode.cpp:1395, :1439-1441 (RK64 ignores the mask)
         if (lane == 0) {
-          a.FC.p[oF] = 0.0;
+          a.FC.p[ad.oF] = 0.0;
           if (status) status[c] = 0;
+          atomicAdd(gstats + 8, 1ull);
         }
-        nskipped++;
         continue;
       }
-      double ry0[NSLOT], y[NSLOT];
-      double Tin = a.T.p[oT];
-      const double rhoe_init = a.rE.p[oE], rhoesrc = a.rEsrc.p[oEs];
+      double y[NSLOT];
+      const double Tin = a.T.p[ad.oT];
+      const double rhoe_init = a.rE.p[ad.oE], rhoesrc = a.rEsrc.p[ad.oEs];
       __syncwarp();
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        const int k = lane + 32 * s;
-        ry0[s] = (k < ns) ? a.rY.p[oY + int64_t(k) * sY] : 0.0;
-        wb[L::SRC + k] = (k < ns) ? a.rYsrc.p[oS + int64_t(k) * sS] : 0.0;
-      }
-      if (lane == 0) {
-        wb[L::SM + 24] = rhoe_init;
-        wb[L::SM + 25] = rhoesrc;
-      }
       const bool clean = (INTEG == kIntegCvode) && o.clean_init_massfrac && !a.flat;
-      double rho_old = 0.0, rho_oldclipped = 0.0, clipped[NSLOT];
-      if (clean) {
-        double p = 0.0;
+      double rho_old = 0.0;
+      {
+        double ry0[NSLOT];
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) p += ry0[s];
-        rho_old = warp_sum(p);
-      }
-      double part = 0.0;
+        for (int s = 0; s < NSLOT; ++s) {
+          const int k = lane + 32 * s;
+          ry0[s] = (k < ns) ? a.rY.p[ad.oY + int64_t(k) * ad.sY] : 0.0;
+          wb[L::SRC + k] = (k < ns) ? a.rYsrc.p[ad.oS + int64_t(k) * ad.sS] : 0.0;
+          wb[L::RY0 + k] = ry0[s];
+        }
+        if (lane == 0) {
+          wb[L::SM + 24] = rhoe_init;
+          wb[L::SM + 25] = rhoesrc;
+        }
+        if (clean) {
+          double p = 0.0;
 #pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        const int k = lane + 32 * s;
-        y[s] = clean ? fmin(fmax(0.0, ry0[s]), rho_old) : ry0[s];
-        if (k >= ns) y[s] = 0.0;
-        clipped[s] = y[s];
-        part += y[s];
+          for (int s = 0; s < NSLOT; ++s) p += ry0[s];
+          rho_old = warp_sum(p);
+        }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          const int k = lane + 32 * s;
+          y[s] = clean ? fmin(fmax(0.0, ry0[s]), rho_old) : ry0[s];
+          if (k >= ns) y[s] = 0.0;
+          wb[L::CLIP + k] = y[s];
+        }
       }
-      double T0 = Tin;
+      double T0 = Tin, rho_oldclipped = 0.0;
       if (!a.flat) {  // box_flatten: T <- RHY2T(rho, rhoH/rho, Y, T_guess)
+        double part = 0.0;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) part += y[s];
         const double rho = warp_sum(part);
         rho_oldclipped = rho;
         const double rho_inv = 1.0 / rho;
@@ -217,6 +239,10 @@ __global__ void __launch_bounds__(kReactThreads, PLM_MIN_BLOCKS)
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         if (lane + 32 * s == ns) y[s] = T0;
+      if (lane == 0) {  // kept for box_unflatten in the scalar area (beyond the integrator's entries)
+        wb[L::SM + 56] = rho_old;
+        wb[L::SM + 57] = rho_oldclipped;
+      }
       __syncwarp();
 
       CellStats st{};
@@ -230,12 +256,15 @@ __global__ void __launch_bounds__(kReactThreads, PLM_MIN_BLOCKS)
         st.nst = fc;
         st.nfe = nfe;
       }
-      // box_unflatten
+      // box_unflatten (addresses recomputed: nothing of the cell's bookkeeping stays live across the integration)
+      ad = cell_addr<L>(a, c);
+      const double rhoe0 = wb[L::SM + 24], rhoesrc0 = wb[L::SM + 25];
       double outv[NSLOT], p2 = 0.0;
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) {
         const int k = lane + 32 * s;
-        outv[s] = clean ? ry0[s] + (y[s] - clipped[s]) * rho_old / rho_oldclipped : y[s];
+        outv[s] = y[s];
+        if (clean) outv[s] = wb[L::RY0 + k] + (y[s] - wb[L::CLIP + k]) * wb[L::SM + 56] / wb[L::SM + 57];
         if (k < ns) p2 += outv[s];
       }
       double Tout = 0.0;
@@ -243,7 +272,7 @@ __global__ void __launch_bounds__(kReactThreads, PLM_MIN_BLOCKS)
       for (int s = 0; s < NSLOT; ++s)
         if (lane + 32 * s == ns) Tout = y[s];
       Tout = __shfl_sync(kFull, Tout, ns & 31);
-      const double rE_new = __dadd_rn(rhoe_init, __dmul_rn(a.dt, rhoesrc));  // unfused, as the host compiler evaluates ReactorUtils.H:180
+      const double rE_new = __dadd_rn(rhoe0, __dmul_rn(a.dt, rhoesrc0));  // unfused, as the host compiler evaluates ReactorUtils.H:180
       if (!a.flat) {
         const double rho = warp_sum(p2);
         const double rho_inv = 1.0 / rho;
@@ -255,29 +284,25 @@ __global__ void __launch_bounds__(kReactThreads, PLM_MIN_BLOCKS)
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) {
         const int k = lane + 32 * s;
-        if (k < ns) a.rY.p[oY + int64_t(k) * sY] = outv[s];
+        if (k < ns) a.rY.p[ad.oY + int64_t(k) * ad.sY] = outv[s];
       }
       if (lane == 0) {
-        a.T.p[oT] = Tout;
-        a.rE.p[oE] = rE_new;
-        a.FC.p[oF] = double(fc);
+        a.T.p[ad.oT] = Tout;
+        a.rE.p[ad.oE] = rE_new;
+        a.FC.p[ad.oF] = double(fc);
         if (status) status[c] = st.flag;
+        atomicAdd(gstats + 0, (unsigned long long)st.nst);
+        atomicAdd(gstats + 1, (unsigned long long)st.nfe);
+        if (st.nje) atomicAdd(gstats + 2, (unsigned long long)st.nje);
+        if (st.nsetups) atomicAdd(gstats + 3, (unsigned long long)st.nsetups);
+        if (st.nni) atomicAdd(gstats + 4, (unsigned long long)st.nni);
+        if (st.ncfn) atomicAdd(gstats + 5, (unsigned long long)st.ncfn);
+        if (st.netf) atomicAdd(gstats + 6, (unsigned long long)st.netf);
+        if (st.flag != 0) atomicAdd(gstats + 7, 1ull);
+        atomicAdd(gstats + 9, 1ull);
+        atomicMax(gstats + 10, (unsigned long long)fc);
+        atomicMax(gstats + 11, 0xffffffffull - (unsigned long long)fc);
       }
-      acc[0] += st.nst; acc[1] += st.nfe; acc[2] += st.nje; acc[3] += st.nsetups;
-      acc[4] += st.nni; acc[5] += st.ncfn; acc[6] += st.netf; acc[7] += (st.flag != 0);
-      maxfc = max(maxfc, fc);
-      minfc = min(minfc, fc);
-      ndone++;
-    }
-  }
-  if (lane == 0) {
-    for (int i = 0; i < 8; ++i)
-      if (acc[i]) atomicAdd(gstats + i, acc[i]);
-    if (nskipped) atomicAdd(gstats + 8, nskipped);
-    if (ndone) {
-      atomicAdd(gstats + 9, ndone);
-      atomicMax(gstats + 10, (unsigned long long)maxfc);
-      atomicMax(gstats + 11, 0xffffffffull - (unsigned long long)minfc);
     }
   }
 }
@@ -417,6 +442,23 @@ size_t react_smem_bytes(const DevMech& m, int integ, int qmax, int warps_per_blo
 {
   size_t v = 0;
   SmemQuery q{warps_per_block, &v};
+  dispatch(m, integ, qmax, q);
+  return v;
+}
+
+struct ThreadsQuery {
+  int* out;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    *out = L::WARPS * 32;
+    return cudaSuccess;
+  }
+};
+int react_threads(const DevMech& m, int integ, int qmax)
+{
+  int v = 0;
+  ThreadsQuery q{&v};
   dispatch(m, integ, qmax, q);
   return v;
 }

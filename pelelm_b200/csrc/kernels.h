@@ -10,7 +10,7 @@
 
 namespace plm {
 
-constexpr int kReactThreads = 128;   // 4 warps = 4 cells in flight per CTA
+constexpr int kReactThreads = 128;   // rhs / jac test kernels: 4 warps = 4 cells in flight per CTA (integration kernel: Lay<>::WARPS)
 constexpr int kCellsPerGrab = 4;     // consecutive cells a warp takes from the queue at once
 constexpr int kIntegCvode = 0, kIntegRK64 = 1;
 constexpr int kMaxN = 64;
@@ -39,6 +39,7 @@ struct LaunchCfg {
 // m: host copy of the descriptor (dimensions for dispatch); dm: its device copy (what the kernels read)
 size_t react_smem_bytes(const DevMech& m, int integ, int qmax, int warps_per_block);
 size_t react_jsave_doubles(const DevMech& m);
+int react_threads(const DevMech& m, int integ, int qmax);  // CTA size of the integration kernel for this mechanism
 int react_occupancy(const DevMech& m, int integ, int qmax, int threads, size_t smem);
 cudaError_t launch_react(const DevMech& m, const DevMech* dm, const ReactOpts& o, const BoxArgs& a, const LaunchCfg& cfg,
                          int integ, unsigned long long* counter, unsigned long long* gstats, int* status,
