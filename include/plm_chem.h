@@ -67,6 +67,26 @@ int  plm_react_box(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rY, p
 int  plm_react_flat(plm_reactor*, double* rY, double* rYsrc, double* rX, double* rX_src,
                     double* dt_react, double* time, int ncells, void* cuda_stream);
 
+/* The body of PeleLM::advance_chemistry's MFIter loop fused into the integration kernel (PeleLM.cpp:5736-5775) plus the
+ * I_R update that follows it (PeleLM.cpp:5783-5800).  All arrays are MKS, as PeleLM holds them:
+ *   load :  rhoY, frc_rhoY x 1e-3 ; rhoH, frc_rhoH x 10      (MKS -> CGS, :5737-5746; the forcing arrays are NOT modified:
+ *                                                              the reference scales a private copy, FTemp)
+ *   react:  exactly plm_react_box (time = 0, dt_react = dt)
+ *   store:  rhoY x 1e3 ; rhoH x 0.1                           (CGS -> MKS, :5765-5772); T, FC as react() leaves them
+ *   I_R  :  -(rhoY_old - rhoY_new) * (1/dt) - frc_rhoY        (:5795-5799), N components; I_R.p == NULL: skipped
+ * Cells with mask == -1 get the same x1e-3 x1e3 / x10 x0.1 round trip the reference applies to them.
+ * Saves the three extra passes over (2N+4) components of the reference sequence. Same pointer / stream rules as
+ * plm_react_box. */
+int  plm_advance_chemistry_box(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
+                               plm_a4d frc_rhoY, plm_a4d frc_rhoH, plm_a4d I_R, plm_a4d FC, plm_a4i mask, double dt,
+                               void* cuda_stream);
+
+/* reactionRateRhoY over a box (PeleLM_K.H:57-101, called by PeleLM::compute_instantaneous_reaction_rates,
+ * PeleLM.cpp:2010-2070): MKS rhoY (N comps), rhoH, T (guess) -> rhoYdot = W_k * wdot_k in kg/m^3/s (N comps);
+ * mask < 0 (EB covered) => 0.  T is not modified. */
+int  plm_reaction_rate_rhoY(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
+                            plm_a4i mask, plm_a4d rhoYdot, void* cuda_stream);
+
 /* waits for every outstanding call of this reactor, then returns and clears the accumulated counters */
 int  plm_reactor_stats(plm_reactor*, plm_stats* out);
 /* status word per cell of the last call, in box order (device or host destination) */

@@ -465,3 +465,27 @@ void orc_rhs(const plm_mech_tables* m, double dt_save, const double* y, double* 
   }
   ydot[ns] = rhoesrc * (rho_inv / cp);
 }
+
+/* reactionRateRhoY for one cell (reference Source/PeleLM_K.H:57-101): MKS rhoY[ns], rhoH, T guess -> rhoYdot[ns] MKS.
+ * HY2T -> GET_T_GIVEN_HY (Fuego.H:120-126); RTY2WDOT (Fuego.H:168-183) = CKYTCR, CKWC, x mw. */
+void orc_reaction_rate_rhoY(const plm_mech_tables* m, const double* rhoY, double rhoH, double T, int mask, double* rhoYdot)
+{
+  const int ns = m->ns;
+  if (mask < 0) {
+    for (int n = 0; n < ns; n++) rhoYdot[n] = 0.0;
+    return;
+  }
+  double rho = 0.0;
+  for (int n = 0; n < ns; n++) rho += rhoY[n];
+  const double rhoinv = 1.0 / rho;
+  double y[ORC_MAXS], C[ORC_MAXS], wdot[ORC_MAXS];
+  for (int n = 0; n < ns; n++) y[n] = rhoY[n] * rhoinv;
+  double Tloc = T;
+  const double H = rhoH * rhoinv * 1.0e4;
+  orc_get_T_given_hY(m, H, y, &Tloc);
+  rho = rho * 0.001;
+  for (int i = 0; i < ns; ++i) C[i] = rho * y[i] * (1.0 / m->mw[i]);
+  orc_ckwc(m, Tloc, C, wdot);
+  for (int n = 0; n < ns; n++) wdot[n] *= m->mw[n];
+  for (int n = 0; n < ns; n++) rhoYdot[n] = wdot[n] * 1000.0;
+}

@@ -27,6 +27,7 @@ void orc_production_rate(const plm_mech_tables* m, double* wdot, const double* s
 void orc_ckwc(const plm_mech_tables* m, double T, const double* C, double* wdot);
 void orc_ajacobian_consP(const plm_mech_tables* m, double* J, const double* sc, double T);
 void orc_cjac(const plm_mech_tables* m, const double* y, double* Jout);
+void orc_reaction_rate_rhoY(const plm_mech_tables* m, const double* rhoY, double rhoH, double T, int mask, double* rhoYdot);
 void orc_rhs(const plm_mech_tables* m, double dt_save, const double* y, double* ydot, double rhoe_init,
              double rhoesrc_ext, const double* rYs);
 

@@ -82,6 +82,7 @@ class Ref:
         L.ref_thermo.argtypes = [C.c_int] + [c_dp] * 5
         L.ref_pty2rh.argtypes = [C.c_int, C.c_double] + [c_dp] * 4
         L.ref_set_typ_vals.argtypes = [c_dp]
+        L.ref_reaction_rate_rhoY.argtypes = [C.c_int] * 3 + [c_dp] * 3 + [c_ip, c_dp]
         buf = C.create_string_buffer(8192)
         L.ref_species_names(buf, 8192)
         self.species = buf.value.decode().split()
@@ -107,6 +108,13 @@ class Ref:
         self.L.ref_react_box(nc, 1, 1, _p(rY), _p(np.ascontiguousarray(rYsrc)), _p(T), _p(rE),
                              _p(np.ascontiguousarray(rEsrc)), _p(FC), _pi(mask), dt, time)
         return rY, T, rE, FC
+
+    def reaction_rate_rhoY(self, rhoY, rhoH, T, mask):
+        """The reference's own reactionRateRhoY (Source/PeleLM_K.H:57-101) over an nc x 1 x 1 box; SoA [ns][nc], MKS."""
+        nc = T.size
+        out = np.zeros_like(rhoY)
+        self.L.ref_reaction_rate_rhoY(nc, 1, 1, _p(rhoY), _p(rhoH), _p(T), _pi(mask), _p(out))
+        return out
 
     def rhs(self, y, rhoe, rhoesrc, rYsrc, t=0.0):
         nc = y.shape[0]
@@ -139,6 +147,22 @@ class Ref:
         rho, h = np.zeros(nc), np.zeros(nc)
         self.L.ref_pty2rh(nc, p, _p(T), _p(Y), _p(rho), _p(h))
         return rho, h
+
+
+def advance_chemistry_soa(R, rhoY, rhoH, T, frc_rhoY, frc_rhoH, mask, dt, **kw):
+    """The body of PeleLM::advance_chemistry around a checker's react (R = Ref or Port), all arrays MKS, SoA [ns][nc]:
+    MKS -> CGS (PeleLM.cpp:5737-5746), react (:5752), CGS -> MKS (:5765-5772), I_R = -(old - new)/dt - F (:5792-5799).
+    Returns rhoY_new, rhoH_new, T_new, FC, I_R."""
+    rY = rhoY * 1.0e-3
+    fY = frc_rhoY * 1.0e-3
+    rH = rhoH * 10.0
+    fH = frc_rhoH * 10.0
+    rY2, T2, rE2, FC = R.react_soa(rY, fY, T, rH, fH, mask, dt, **kw)
+    rY_new = rY2 * 1.0e3
+    rH_new = rE2 * 0.1
+    dt_inv = 1.0 / dt
+    I_R = -(rhoY - rY_new) * dt_inv - frc_rhoY
+    return rY_new, rH_new, T2, FC, I_R
 
 
 class Port:
@@ -208,6 +232,17 @@ class Port:
         if return_stats:
             return rY, T, rE, FC, st.as_dict()
         return rY, T, rE, FC
+
+    def reaction_rate_rhoY(self, rhoY, rhoH, T, mask):
+        nc = T.size
+        out = np.zeros_like(rhoY)
+        col = np.zeros(self.ns)
+        self.L.orc_reaction_rate_rhoY.argtypes = [C.c_void_p, c_dp, C.c_double, C.c_double, C.c_int, c_dp]
+        for c in range(nc):
+            self.L.orc_reaction_rate_rhoY(self.m, _p(np.ascontiguousarray(rhoY[:, c])), float(rhoH[c]), float(T[c]),
+                                          int(mask[c]), _p(col))
+            out[:, c] = col
+        return out
 
     def rhs(self, y, rhoe, rhoesrc, rYsrc, t=0.0):
         out = np.zeros_like(y)

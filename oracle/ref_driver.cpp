@@ -11,6 +11,7 @@
 //   utils::fKernelSpec                        PelePhysics/Reactions/ReactorUtils.H:274-332
 //   cvode::cJac                               PelePhysics/Reactions/ReactorCvodeJacobian.cpp:84-153
 //   CKWC / GET_T_GIVEN_HY / CKHMS / CKCPBS    Support/Mechanism/Models/<mech>/mechanism.H
+//   reactionRateRhoY                          Source/PeleLM_K.H:57-101 (the reference's own inline function)
 #include <AMReX.H>
 #include <AMReX_ParmParse.H>
 #include <AMReX_Box.H>
@@ -23,6 +24,7 @@
 #include "ReactorUtils.H"
 #include "ReactorCvodeUtils.H"
 #include "ReactorCvodeJacobian.H"
+#include "PeleLM_K.H"  // reference Source/PeleLM_K.H (header only: reactionRateRhoY :57-101)
 
 #include <sunmatrix/sunmatrix_dense.h>
 #include <nvector/nvector_serial.h>
@@ -118,6 +120,24 @@ int ref_react_box(int nx, int ny, int nz, double* rY, double* rYsrc, double* T, 
   amrex::Real dt_react = dt;
   amrex::Real t = time;
   return g_reactor->react(box, a_rY, a_rYsrc, a_T, a_rE, a_rEsrc, a_FC, a_mask, dt_react, t);
+}
+
+// reactionRateRhoY (PeleLM_K.H:57-101) over an nx*ny*nz box, FAB layout, MKS in and out.
+void ref_reaction_rate_rhoY(int nx, int ny, int nz, const double* rhoY, const double* rhoH, const double* T,
+                            const int* mask, double* rhoYdot)
+{
+  amrex::Box box(amrex::IntVect(0, 0, 0), amrex::IntVect(nx - 1, ny - 1, nz - 1));
+  const amrex::Dim3 lo = amrex::lbound(box);
+  amrex::Dim3 hi = amrex::ubound(box);
+  hi.x += 1; hi.y += 1; hi.z += 1;
+  amrex::Array4<const amrex::Real> a_rY(rhoY, lo, hi, NUM_SPECIES);
+  amrex::Array4<const amrex::Real> a_rH(rhoH, lo, hi, 1);
+  amrex::Array4<const amrex::Real> a_T(T, lo, hi, 1);
+  amrex::Array4<const int> a_mask(mask, lo, hi, 1);
+  amrex::Array4<amrex::Real> a_out(rhoYdot, lo, hi, NUM_SPECIES);
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) reactionRateRhoY(i, j, k, a_rY, a_rH, a_T, a_mask, a_out);
 }
 
 // Flat (1dArray) API: rY [ncells][N+1] incl. T, rYsrc [ncells][N], rX/rX_src [ncells].

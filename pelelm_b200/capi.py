@@ -40,6 +40,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals", "plm_react_box", "plm_react_flat",
+           "plm_advance_chemistry_box", "plm_reaction_rate_rhoY",
            "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
            "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_measure_fp64_peak", "plm_species_name"]
 
@@ -61,6 +62,8 @@ def load():
                                    C.c_int, C.c_int, C.c_int]
     L.plm_reactor_set_typ_vals.argtypes = [vp, c_dp, C.c_int]
     L.plm_react_box.argtypes = [vp, c_ip, c_ip, A4D, A4D, A4D, A4D, A4D, A4D, A4I, c_dp, c_dp, vp]
+    L.plm_advance_chemistry_box.argtypes = [vp, c_ip, c_ip, A4D, A4D, A4D, A4D, A4D, A4D, A4D, A4I, C.c_double, vp]
+    L.plm_reaction_rate_rhoY.argtypes = [vp, c_ip, c_ip, A4D, A4D, A4D, A4I, A4D, vp]
     L.plm_react_flat.argtypes = [vp, vp, vp, vp, vp, c_dp, c_dp, C.c_int, vp]
     L.plm_reactor_stats.argtypes = [vp, C.POINTER(Stats)]
     L.plm_reactor_cell_status.argtypes = [vp, vp, C.c_int64]
@@ -188,6 +191,36 @@ class Reactor:
         self._chk(self.L.plm_react_box(self.h, lo, hi, *a, m, C.cast(C.byref(dt), c_dp), C.cast(C.byref(tm), c_dp),
                                        C.c_void_p(stream or 0)))
         return self.stats() if sync else None
+
+    def advance_chemistry(self, box_lo, box_hi, rhoY, rhoH, T, frc_rhoY, frc_rhoH, I_R, FC, mask, dt, fab_lo=None,
+                          fab_hi=None, stream=None, sync=True):
+        """The fused body of PeleLM::advance_chemistry (PeleLM.cpp:5736-5800): MKS arrays; rhoY, rhoH, T, FC updated in
+        place, I_R written (pass None to skip), forcing read only."""
+        fab_lo = list(box_lo if fab_lo is None else fab_lo)
+        fab_hi = list(box_hi if fab_hi is None else fab_hi)
+        ns = self.ns
+        lo = (C.c_int * 3)(*box_lo)
+        hi = (C.c_int * 3)(*box_hi)
+        ir = A4D() if I_R is None else self._a4(A4D, I_R, fab_lo, fab_hi, ns)
+        m = A4I() if mask is None else self._a4(A4I, mask, fab_lo, fab_hi, 1)
+        self._chk(self.L.plm_advance_chemistry_box(
+            self.h, lo, hi, self._a4(A4D, rhoY, fab_lo, fab_hi, ns), self._a4(A4D, rhoH, fab_lo, fab_hi, 1),
+            self._a4(A4D, T, fab_lo, fab_hi, 1), self._a4(A4D, frc_rhoY, fab_lo, fab_hi, ns),
+            self._a4(A4D, frc_rhoH, fab_lo, fab_hi, 1), ir, self._a4(A4D, FC, fab_lo, fab_hi, 1), m, float(dt),
+            C.c_void_p(stream or 0)))
+        return self.stats() if sync else None
+
+    def reaction_rate_rhoY(self, box_lo, box_hi, rhoY, rhoH, T, mask, rhoYdot, fab_lo=None, fab_hi=None, stream=None):
+        """reactionRateRhoY over a box (PeleLM_K.H:57-101): MKS in, rhoYdot (N comps, kg/m^3/s) out."""
+        fab_lo = list(box_lo if fab_lo is None else fab_lo)
+        fab_hi = list(box_hi if fab_hi is None else fab_hi)
+        ns = self.ns
+        lo = (C.c_int * 3)(*box_lo)
+        hi = (C.c_int * 3)(*box_hi)
+        m = A4I() if mask is None else self._a4(A4I, mask, fab_lo, fab_hi, 1)
+        self._chk(self.L.plm_reaction_rate_rhoY(
+            self.h, lo, hi, self._a4(A4D, rhoY, fab_lo, fab_hi, ns), self._a4(A4D, rhoH, fab_lo, fab_hi, 1),
+            self._a4(A4D, T, fab_lo, fab_hi, 1), m, self._a4(A4D, rhoYdot, fab_lo, fab_hi, ns), C.c_void_p(stream or 0)))
 
     def react_flat(self, rY, rYsrc, rX, rX_src, dt_react, time=0.0, stream=None):
         ncells = int(np.prod(rX.shape))

@@ -93,7 +93,7 @@ struct plm_reactor {
   CallSlot slot[kSlots];
   int next_slot = 0, last_slot = -1;
   unsigned long long* host_stats = nullptr;  // pinned
-  DevBuf stage[7]; // host-pointer staging: rY rYsrc T rE rEsrc FC mask
+  DevBuf stage[8]; // host-pointer staging: rY rYsrc T rE rEsrc FC mask I_R
   DevBuf scratch[6];
   plm_stats last{};
   double pending_ms = 0.0;  // kernel time of completed-but-unreported calls
@@ -306,9 +306,13 @@ size_t a4_count(const plm_a4d& a) { return size_t(a.nstride) * size_t(std::max(a
 
 extern "C" {
 
-int plm_react_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, plm_a4d rYsrc, plm_a4d T,
-                  plm_a4d rEner, plm_a4d rEner_src, plm_a4d FC, plm_a4i mask, double* dt_react, double* time,
-                  void* cuda_stream)
+}  // extern "C"
+
+namespace {
+// react over a box; mks != 0: the fused PeleLM::advance_chemistry body (MKS arrays, optional I_R output)
+int react_box_impl(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, plm_a4d rYsrc, plm_a4d T,
+                   plm_a4d rEner, plm_a4d rEner_src, plm_a4d FC, plm_a4i mask, const double* dt_react,
+                   const double* time, void* cuda_stream, int mks, plm_a4d IR)
 {
   if (!r || !lo || !hi || !dt_react || !time) return fail(PLM_ERR_ARG, "null argument");
   if (!r->inited) return fail(PLM_ERR_ARG, "plm_reactor_init has not been called");
@@ -334,8 +338,17 @@ int plm_react_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, 
   a.time = *time;
   const bool dev = is_device_ptr(rY.p);
   a.rY = rY; a.rYsrc = rYsrc; a.T = T; a.rE = rEner; a.rEsrc = rEner_src; a.FC = FC; a.mask = mask;
+  a.mks = mks;
+  a.IR = IR;
+  a.dt_inv = 1.0 / a.dt;
+  if (IR.p) {
+    if (IR.ncomp < ns) return fail(PLM_ERR_ARG, "I_R needs NUM_SPECIES components");
+    for (int d = 0; d < 3; ++d)
+      if (lo[d] < IR.lo[d] || hi[d] > IR.hi[d]) return fail(PLM_ERR_ARG, "box is not contained in I_R bounds");
+  }
   if (!dev) {
     int rc;
+    if (IR.p && (rc = stage_in(r->stage[7], IR.p, a4_count(IR), &a.IR.p, st, true))) return rc;
     if ((rc = stage_in(r->stage[0], rY.p, a4_count(rY), &a.rY.p, st, true))) return rc;
     if ((rc = stage_in(r->stage[1], rYsrc.p, a4_count(rYsrc), &a.rYsrc.p, st, true))) return rc;
     if ((rc = stage_in(r->stage[2], T.p, a4_count(T), &a.T.p, st, true))) return rc;
@@ -354,6 +367,68 @@ int plm_react_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, 
     PLM_CUDA(cudaMemcpyAsync(T.p, a.T.p, a4_count(T) * sizeof(double), cudaMemcpyDeviceToHost, st));
     PLM_CUDA(cudaMemcpyAsync(rEner.p, a.rE.p, a4_count(rEner) * sizeof(double), cudaMemcpyDeviceToHost, st));
     PLM_CUDA(cudaMemcpyAsync(FC.p, a.FC.p, a4_count(FC) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (IR.p) PLM_CUDA(cudaMemcpyAsync(IR.p, a.IR.p, a4_count(IR) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaStreamSynchronize(st));
+  }
+  return PLM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int plm_react_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, plm_a4d rYsrc, plm_a4d T,
+                  plm_a4d rEner, plm_a4d rEner_src, plm_a4d FC, plm_a4i mask, double* dt_react, double* time,
+                  void* cuda_stream)
+{
+  return react_box_impl(r, lo, hi, rY, rYsrc, T, rEner, rEner_src, FC, mask, dt_react, time, cuda_stream, 0, plm_a4d{});
+}
+
+int plm_advance_chemistry_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
+                              plm_a4d frc_rhoY, plm_a4d frc_rhoH, plm_a4d I_R, plm_a4d FC, plm_a4i mask, double dt,
+                              void* cuda_stream)
+{
+  const double time = 0.0;  // PeleLM.cpp:5751
+  return react_box_impl(r, lo, hi, rhoY, frc_rhoY, T, rhoH, frc_rhoH, FC, mask, &dt, &time, cuda_stream, 1, I_R);
+}
+
+int plm_reaction_rate_rhoY(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
+                           plm_a4i mask, plm_a4d rhoYdot, void* cuda_stream)
+{
+  if (!r || !lo || !hi) return fail(PLM_ERR_ARG, "null argument");
+  if (!rhoY.p || !rhoH.p || !T.p || !rhoYdot.p) return fail(PLM_ERR_ARG, "null array");
+  const int ns = r->tables->ns;
+  if (rhoY.ncomp < ns || rhoYdot.ncomp < ns) return fail(PLM_ERR_ARG, "rhoY/rhoYdot need NUM_SPECIES components");
+  for (int d = 0; d < 3; ++d) {
+    if (hi[d] < lo[d]) return PLM_OK;
+    const plm_a4d* arrs[4] = {&rhoY, &rhoH, &T, &rhoYdot};
+    for (auto* a : arrs)
+      if (lo[d] < a->lo[d] || hi[d] > a->hi[d]) return fail(PLM_ERR_ARG, "box is not contained in an array's bounds");
+    if (mask.p && (lo[d] < mask.lo[d] || hi[d] > mask.hi[d])) return fail(PLM_ERR_ARG, "box is not contained in mask bounds");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  plm::BoxArgs a{};
+  for (int d = 0; d < 3; ++d) {
+    a.lo[d] = lo[d];
+    a.hi[d] = hi[d];
+  }
+  a.ncells = int64_t(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+  a.rY = rhoY; a.rE = rhoH; a.T = T; a.mask = mask;
+  plm_a4d out = rhoYdot;
+  const bool dev = is_device_ptr(rhoY.p);
+  if (!dev) {
+    int rc;
+    if ((rc = stage_in(r->stage[0], rhoY.p, a4_count(rhoY), &a.rY.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[2], T.p, a4_count(T), &a.T.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[3], rhoH.p, a4_count(rhoH), &a.rE.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[1], rhoYdot.p, a4_count(rhoYdot), &out.p, st, true))) return rc;
+    if (mask.p) {
+      const size_t cnt = size_t(mask.nstride) * size_t(std::max(mask.ncomp, 1));
+      if ((rc = stage_in(r->stage[6], mask.p, cnt, &a.mask.p, st, true))) return rc;
+    }
+  }
+  PLM_CUDA(plm::launch_reaction_rate(r->mech.h, r->mech.d, a, out, st));
+  if (!dev) {
+    PLM_CUDA(cudaMemcpyAsync(rhoYdot.p, out.p, a4_count(rhoYdot) * sizeof(double), cudaMemcpyDeviceToHost, st));
     PLM_CUDA(cudaStreamSynchronize(st));
   }
   return PLM_OK;

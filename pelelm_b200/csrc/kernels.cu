@@ -111,7 +111,7 @@ __device__ __forceinline__ int64_t a4_off(const plm_a4d& a, int i, int j, int k)
 
 // where cell c of the call lives in the caller's arrays (FAB layout, or the flat AoS layout of the 1dArray API)
 struct CellAddr {
-  int64_t oY, oS, oT, oE, oEs, oF, sY, sS;
+  int64_t oY, oS, oT, oE, oEs, oF, oI, sY, sS;
   int mk;
 };
 template <class L>
@@ -121,7 +121,7 @@ __device__ __noinline__ CellAddr cell_addr(const BoxArgs& a, int64_t c)
   CellAddr r;
   r.mk = 1;
   if (a.flat) {
-    r.oY = c * n; r.oS = c * ns; r.oT = c * n + ns; r.oE = c; r.oEs = c; r.oF = c; r.sY = 1; r.sS = 1;
+    r.oY = c * n; r.oS = c * ns; r.oT = c * n + ns; r.oE = c; r.oEs = c; r.oF = c; r.oI = 0; r.sY = 1; r.sS = 1;
   } else {
     const int nx = a.hi[0] - a.lo[0] + 1, ny = a.hi[1] - a.lo[1] + 1;
     const int i = a.lo[0] + int(c % nx), j = a.lo[1] + int((c / nx) % ny), k = a.lo[2] + int(c / (int64_t(nx) * ny));
@@ -131,6 +131,7 @@ __device__ __noinline__ CellAddr cell_addr(const BoxArgs& a, int64_t c)
     r.oE = a4_off(a.rE, i, j, k);
     r.oEs = a4_off(a.rEsrc, i, j, k);
     r.oF = a4_off(a.FC, i, j, k);
+    r.oI = a.IR.p ? a4_off(a.IR, i, j, k) : 0;
     if (a.mask.p) r.mk = a.mask.p[int64_t(i - a.mask.lo[0]) + int64_t(j - a.mask.lo[1]) * a.mask.jstride +
                                   int64_t(k - a.mask.lo[2]) * a.mask.kstride];
   }
@@ -188,11 +189,29 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
           if (status) status[c] = 0;
           atomicAdd(gstats + 8, 1ull);
         }
+        if (a.mks) {  // the reference still scales a skipped cell to CGS and back (PeleLM.cpp:5737-5772): same roundings
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s) {
+            const int k = lane + 32 * s;
+            if (k < ns) {
+              double* dst = a.rY.p + ad.oY + int64_t(k) * ad.sY;
+              const double vold = *dst, vnew = __dmul_rn(__dmul_rn(vold, 1.0e-3), 1.0e3);
+              if (a.IR.p)
+                a.IR.p[ad.oI + int64_t(k) * a.IR.nstride] =
+                    __dsub_rn(__dmul_rn(-__dsub_rn(vold, vnew), a.dt_inv), a.rYsrc.p[ad.oS + int64_t(k) * ad.sS]);
+              *dst = vnew;
+            }
+          }
+          if (lane == 0) a.rE.p[ad.oE] = __dmul_rn(__dmul_rn(a.rE.p[ad.oE], 10.0), 0.1);
+        }
         continue;
       }
       double y[NSLOT];
       const double Tin = a.T.p[ad.oT];
-      const double rhoe_init = a.rE.p[ad.oE], rhoesrc = a.rEsrc.p[ad.oEs];
+      const bool mks = a.mks != 0;
+      // __dmul_rn / __dadd_rn: the scalings are separate, rounded operations in the reference (no contraction into FMAs)
+      const double rhoe_init = mks ? __dmul_rn(a.rE.p[ad.oE], 10.0) : a.rE.p[ad.oE];
+      const double rhoesrc = mks ? __dmul_rn(a.rEsrc.p[ad.oEs], 10.0) : a.rEsrc.p[ad.oEs];
       __syncwarp();
       const bool clean = (INTEG == kIntegCvode) && o.clean_init_massfrac && !a.flat;
       double rho_old = 0.0;
@@ -202,7 +221,12 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
         for (int s = 0; s < NSLOT; ++s) {
           const int k = lane + 32 * s;
           ry0[s] = (k < ns) ? a.rY.p[ad.oY + int64_t(k) * ad.sY] : 0.0;
-          wb[L::SRC + k] = (k < ns) ? a.rYsrc.p[ad.oS + int64_t(k) * ad.sS] : 0.0;
+          double sv = (k < ns) ? a.rYsrc.p[ad.oS + int64_t(k) * ad.sS] : 0.0;
+          if (mks) {  // PeleLM.cpp:5737-5746
+            ry0[s] = __dmul_rn(ry0[s], 1.0e-3);
+            sv = __dmul_rn(sv, 1.0e-3);
+          }
+          wb[L::SRC + k] = sv;
           wb[L::RY0 + k] = ry0[s];
         }
         if (lane == 0) {
@@ -284,11 +308,24 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) {
         const int k = lane + 32 * s;
-        if (k < ns) a.rY.p[ad.oY + int64_t(k) * ad.sY] = outv[s];
+        if (k < ns) {
+          double* dst = a.rY.p + ad.oY + int64_t(k) * ad.sY;
+          if (mks) {  // CGS -> MKS (PeleLM.cpp:5765-5772), then I_R (PeleLM.cpp:5795-5799) from the old value still in place
+            const double vnew = __dmul_rn(outv[s], 1.0e3);
+            if (a.IR.p) {
+              const double vold = *dst;
+              const double frc = a.rYsrc.p[ad.oS + int64_t(k) * ad.sS];
+              a.IR.p[ad.oI + int64_t(k) * a.IR.nstride] = __dsub_rn(__dmul_rn(-__dsub_rn(vold, vnew), a.dt_inv), frc);
+            }
+            *dst = vnew;
+          } else {
+            *dst = outv[s];
+          }
+        }
       }
       if (lane == 0) {
         a.T.p[ad.oT] = Tout;
-        a.rE.p[ad.oE] = rE_new;
+        a.rE.p[ad.oE] = mks ? __dmul_rn(rE_new, 0.1) : rE_new;
         a.FC.p[ad.oF] = double(fc);
         if (status) status[c] = st.flag;
         atomicAdd(gstats + 0, (unsigned long long)st.nst);
@@ -359,6 +396,78 @@ __global__ void __launch_bounds__(kReactThreads) jac_kernel(const DevMech* __res
       Jout[size_t(c) * n * n + e] = wb[L::A + row * ld + col];
     }
     __syncwarp();
+  }
+}
+
+// PeleLM_K.H:57-101 reactionRateRhoY, one warp per cell: rho = sum rhoY (MKS), Y, T <- HY2T(rhoH/rho * 1e4, Y; guess T),
+// wdot*W = RTY2WDOT(rho * 1e-3, T, Y) (Fuego.H:168-183: C_k = rho Y_k / W_k, CKWC, x W_k), rhoYdot = x 1000.
+template <class L>
+__global__ void __launch_bounds__(kReactThreads) reaction_rate_kernel(const DevMech* __restrict__ dm, const BoxArgs a,
+                                                                      const plm_a4d out)
+{
+  constexpr int NSLOT = L::NSLOT, ns = L::NS;
+  double* wb = block_prologue<L>(dm);
+  const DevMech& m = smem_mech();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = gridDim.x * (blockDim.x >> 5);
+  const int nx = a.hi[0] - a.lo[0] + 1, ny = a.hi[1] - a.lo[1] + 1;
+  for (int64_t c = blockIdx.x * (blockDim.x >> 5) + warp; c < a.ncells; c += nw) {
+    const int i = a.lo[0] + int(c % nx), j = a.lo[1] + int((c / nx) % ny), k3 = a.lo[2] + int(c / (int64_t(nx) * ny));
+    const int64_t oY = a4_off(a.rY, i, j, k3), oO = a4_off(out, i, j, k3);
+    int mk = 1;
+    if (a.mask.p) mk = a.mask.p[int64_t(i - a.mask.lo[0]) + int64_t(j - a.mask.lo[1]) * a.mask.jstride +
+                                int64_t(k3 - a.mask.lo[2]) * a.mask.kstride];
+    __syncwarp();
+    if (mk < 0) {  // EB covered cell: no reactions
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (lane + 32 * s < ns) out.p[oO + int64_t(lane + 32 * s) * out.nstride] = 0.0;
+      continue;
+    }
+    double ry[NSLOT], part = 0.0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int k = lane + 32 * s;
+      ry[s] = (k < ns) ? a.rY.p[oY + int64_t(k) * a.rY.nstride] : 0.0;
+      part += ry[s];
+    }
+    double rho = warp_sum(part);
+    const double rhoinv = 1.0 / rho;
+    double Y[NSLOT], Yw[NSLOT], imw[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int k = lane + 32 * s;
+      imw[s] = ldg(m.imw + k);
+      Y[s] = ry[s] * rhoinv;
+      Yw[s] = (k < ns) ? Y[s] * imw[s] : 0.0;
+    }
+    const double H = a.rE.p[a4_off(a.rE, i, j, k3)] * rhoinv * 1.0e4;
+    double cp;
+    const double T = get_T_given_hY<L>(H, Yw, a.T.p[a4_off(a.T, i, j, k3)], cp);
+    rho = rho * 0.001;
+    const double logT = dlog(T), invT = 1.0 / T;
+    double cpart = 0.0;
+    double2* cg = reinterpret_cast<double2*>(wb + L::CG);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int k = lane + 32 * s;
+      if (k < ns) {
+        const double cc = ((rho * Y[s]) * imw[s]) * 1.0e6;  // CKYTCR (mechanism.H:2403) then CKWC's SI conversion (:4911)
+        cg[k] = make_double2(cc, gibbs_k<L::NP>(m, k, T, logT, invT));
+        cpart += cc;
+      }
+    }
+    const double mixture = warp_sum(cpart);
+    __syncwarp();
+    eval_rates<L>(m, wb, lane, T, logT, invT, mixture);
+    __syncwarp();
+    double wdot[NSLOT];
+    gather_wdot<L>(m, wb, lane, wdot);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int k = lane + 32 * s;
+      if (k < ns) out.p[oO + int64_t(k) * out.nstride] = ((wdot[s] * 1.0e-6) * ldg(m.mw + k)) * 1000.0;
+    }
   }
 }
 
@@ -574,6 +683,30 @@ struct JacLaunch {
 cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const double* y, double* J, cudaStream_t stream)
 {
   JacLaunch l{dm, ncells, y, J, stream};
+  return dispatch(m, kIntegCvode, 2, l);
+}
+
+struct RateLaunch {
+  const DevMech* dm;
+  const BoxArgs& a;
+  plm_a4d out;
+  cudaStream_t stream;
+  template <class L, int IG>
+  cudaError_t run()
+  {
+    const int wpb = kReactThreads / 32;
+    const size_t smem = (size_t(kHdr) + size_t(wpb) * L::TOTAL) * sizeof(double);
+    const int64_t want = (a.ncells + wpb - 1) / wpb;
+    const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8)));
+    cudaError_t e = cudaFuncSetAttribute(reaction_rate_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    reaction_rate_kernel<L><<<blocks, kReactThreads, smem, stream>>>(dm, a, out);
+    return cudaGetLastError();
+  }
+};
+cudaError_t launch_reaction_rate(const DevMech& m, const DevMech* dm, const BoxArgs& a, plm_a4d rhoYdot, cudaStream_t stream)
+{
+  RateLaunch l{dm, a, rhoYdot, stream};
   return dispatch(m, kIntegCvode, 2, l);
 }
 

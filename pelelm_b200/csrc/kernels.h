@@ -29,6 +29,11 @@ struct BoxArgs {
   plm_a4d rY, rYsrc, T, rE, rEsrc, FC;
   plm_a4i mask;
   double dt, time;
+  // PeleLM::advance_chemistry fused mode (PeleLM.cpp:5736-5803): state and forcing are MKS; the kernel scales to CGS on
+  // load (rhoY, F_rhoY x1e-3; rhoH, F_rhoH x10), back on store (x1e3, x0.1) and writes I_R = -(old - new)/dt - F
+  int mks;
+  plm_a4d IR;      // N components, p == nullptr: not wanted
+  double dt_inv;   // 1/dt as the host computes it (PeleLM.cpp:5792)
 };
 
 struct LaunchCfg {
@@ -47,6 +52,8 @@ cudaError_t launch_react(const DevMech& m, const DevMech* dm, const ReactOpts& o
 cudaError_t launch_rhs(const DevMech& m, const DevMech* dm, int ncells, double t, const double* y, const double* rhoe,
                        const double* rhoesrc, const double* rYsrc, double* ydot, cudaStream_t stream);
 cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const double* y, double* J, cudaStream_t stream);
+// PeleLM_K.H:57-101 reactionRateRhoY over a box (MKS in, MKS out; mask < 0 => zero)
+cudaError_t launch_reaction_rate(const DevMech& m, const DevMech* dm, const BoxArgs& a, plm_a4d rhoYdot, cudaStream_t stream);
 cudaError_t launch_dfma_peak(double* scratch, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_box_costs(const double* FC, const int64_t* off, int nboxes, long long* costs, cudaStream_t stream);
 

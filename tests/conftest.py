@@ -41,6 +41,11 @@ def golden(mech):
     return np.load(os.path.join(GOLDEN, mech + ".npz"))
 
 
+def golden_plm(mech):
+    """the PeleLM-side callers of the path (advance_chemistry body, reactionRateRhoY): tests/golden/<mech>_plm.npz"""
+    return np.load(os.path.join(GOLDEN, mech + "_plm.npz"))
+
+
 def scaled_err(a, ref, rtol, atol):
     """max |a-ref| / (rtol*|ref| + atol): <= 1 means within the stated tolerance."""
     return float(np.max(np.abs(a - ref) / (rtol * np.abs(ref) + atol))) if ref.size else 0.0

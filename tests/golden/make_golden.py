@@ -88,6 +88,34 @@ def one(mech: str):
     print(mech, "golden written:", len(out), "arrays")
 
 
+def extra(mech: str):
+    """tests/golden/<mech>_plm.npz: the PeleLM-side callers of the path -- the fused advance_chemistry body
+    (PeleLM.cpp:5736-5800, restated in oracle/pyoracle.py::advance_chemistry_soa around the reference's react) and the
+    reference's own reactionRateRhoY (Source/PeleLM_K.H:57-101)."""
+    from oracle.pyoracle import Ref, advance_chemistry_soa
+    from pelelm_b200 import synth
+    R = Ref(mech)
+    out = {}
+    nc = NCELLS[mech]
+    b = synth.synthetic_batch(mech, nc, seed=synth.DEFAULT_SEED + 101, dt=DT, forcing=True, mask_every=5)
+    R.init(integrator="ReactorCvode", rtol=1e-8, atol=1e-10, max_order=2)
+    R.set_typ_vals(np.full(R.n, -1.0))
+    ins = dict(rhoY=b["rY"] * 1e3, rhoH=b["rE"] * 0.1, T=b["T"], frcY=b["rYsrc"] * 1e3, frcH=b["rEsrc"] * 0.1, mask=b["mask"])
+    res = advance_chemistry_soa(R, ins["rhoY"], ins["rhoH"], ins["T"], ins["frcY"], ins["frcH"], ins["mask"], DT)
+    for k, v in ins.items():
+        out["advchem/in_" + k] = v
+    for k, v in zip(("rhoY", "rhoH", "T", "FC", "IR"), res):
+        out["advchem/" + k] = v
+    b = synth.synthetic_batch(mech, 64, seed=synth.DEFAULT_SEED + 102, dt=DT, mask_every=6)
+    rhoY, rhoH = np.ascontiguousarray(b["rY"] * 1e3), np.ascontiguousarray(b["rE"] * 0.1)
+    mask = b["mask"].copy()
+    mask[mask == -1] = -1
+    out["rrate/rhoY"], out["rrate/rhoH"], out["rrate/T"], out["rrate/mask"] = rhoY, rhoH, b["T"], mask
+    out["rrate/rhoYdot"] = R.reaction_rate_rhoY(rhoY, rhoH, b["T"], mask)
+    np.savez_compressed(os.path.join(HERE, mech + "_plm.npz"), **out)
+    print(mech, "PeleLM-side golden written:", len(out), "arrays")
+
+
 def knap():
     """KnapSackProcessorMap buckets from the reference's own knapsack() (any libref works)."""
     import ctypes as C
@@ -111,8 +139,15 @@ def knap():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 2 and sys.argv[1] == "extra":
+        extra(sys.argv[2])
+    elif len(sys.argv) > 1 and sys.argv[1] == "extra":  # only the PeleLM-side fixtures (the others stay as committed)
+        for m in NCELLS:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "extra", m])
+    elif len(sys.argv) > 1:
         knap() if sys.argv[1] == "knapsack" else one(sys.argv[1])
     else:
         for m in list(NCELLS) + ["knapsack"]:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), m])
+        for m in NCELLS:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "extra", m])

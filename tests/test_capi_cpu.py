@@ -14,7 +14,7 @@ from conftest import ROOT, GOLDEN
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "plm_chem.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(plm_[a-z0-9_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(plm_[A-Za-z0-9_]+)\s*\(", hdr)))
 
 
 def test_header_symbols_exported(plm_lib):

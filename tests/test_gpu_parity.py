@@ -7,7 +7,7 @@ identical mask/skip behaviour; rhoH bit-exact; FC identical where the port's is.
 import numpy as np
 import pytest
 
-from conftest import MECHS, golden, check_state
+from conftest import MECHS, golden, golden_plm, check_state
 from golden.make_golden import CASES, DT
 
 pytestmark = pytest.mark.gpu
@@ -234,3 +234,66 @@ def test_full_size_properties(capi):
     assert rc == 0
     assert np.array_equal(costs.cpu().numpy(), a[5].reshape(nb, -1).sum(1).astype(np.int64))
     R.close()
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_advance_chemistry_fused_vs_reference(capi, port_lib, mech):
+    """plm_advance_chemistry_box = the body of PeleLM::advance_chemistry (PeleLM.cpp:5736-5800) in one kernel pass, against
+    the same sequence run around the reference's react (golden) and around the port's react (live): MKS state, I_R,
+    bit-exact rhoH, the x1e-3 x1e3 round trip of masked cells, forcing arrays untouched."""
+    g = golden_plm(mech)
+    ins = {k: g["advchem/in_" + k].copy() for k in ("rhoY", "rhoH", "T", "frcY", "frcH", "mask")}
+    nc = ins["T"].size
+    R = capi.Reactor(mech, "ReactorCvode").init(rtol=1e-8, atol=1e-10, max_order=2)
+    rhoY, rhoH, T = ins["rhoY"].copy(), ins["rhoH"].copy(), ins["T"].copy()
+    frcY, frcH = ins["frcY"].copy(), ins["frcH"].copy()
+    IR, FC = np.full_like(rhoY, 7.0), np.zeros(nc)
+    st = R.advance_chemistry([0, 0, 0], [nc - 1, 0, 0], rhoY, rhoH, T, frcY, frcH, IR, FC, ins["mask"], DT)
+    assert not R.cell_status(nc).any()
+    R.close()
+    assert np.array_equal(frcY, ins["frcY"]) and np.array_equal(frcH, ins["frcH"])
+    small = mech != "dodecane_lu"
+    ref = (g["advchem/rhoY"], g["advchem/T"], g["advchem/rhoH"], g["advchem/FC"])
+    check_state((rhoY, T, rhoH, FC), ref, 1e-7, tag=mech + "/advchem", rtol=1e-6, fc_equal_min=0.9 if small else None,
+                fc_rel=0.05 if small else 0.15)
+    m = ins["mask"] == -1
+    assert m.any() and st["nskipped"] == int(m.sum())
+    # masked cells: bit-identical to the reference sequence (scaled to CGS and back, T untouched, I_R from that round trip)
+    assert np.array_equal(rhoY[:, m], g["advchem/rhoY"][:, m]) and np.array_equal(T[m], ins["T"][m])
+    assert np.array_equal(IR[:, m], g["advchem/IR"][:, m])
+    # I_R is exactly -(old - new) * (1/dt) - F of the returned state
+    assert np.array_equal(IR, -(ins["rhoY"] - rhoY) * (1.0 / DT) - ins["frcY"])
+    e = np.abs(IR - g["advchem/IR"]) / (1e-6 * np.abs(g["advchem/IR"]) + 1e-6 * np.abs(g["advchem/IR"]).max(0, keepdims=True) + 1e-7 / DT)
+    assert e.max() <= 1.0, e.max()
+    # the same through device pointers, without I_R
+    import torch
+    R = capi.Reactor(mech, "ReactorCvode").init(rtol=1e-8, atol=1e-10, max_order=2)
+    d = {k: torch.from_numpy(v.copy()).cuda() for k, v in ins.items()}
+    FCd = torch.zeros(nc, dtype=torch.float64, device="cuda")
+    R.advance_chemistry([0, 0, 0], [nc - 1, 0, 0], d["rhoY"], d["rhoH"], d["T"], d["frcY"], d["frcH"], None, FCd, d["mask"], DT)
+    torch.cuda.synchronize()
+    R.close()
+    assert np.array_equal(d["rhoY"].cpu().numpy(), rhoY) and np.array_equal(d["rhoH"].cpu().numpy(), rhoH)
+    assert np.array_equal(d["T"].cpu().numpy(), T) and np.array_equal(FCd.cpu().numpy(), FC)
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_reaction_rate_rhoY_vs_reference_and_port(capi, port_lib, mech):
+    """plm_reaction_rate_rhoY vs the reference's own reactionRateRhoY (Source/PeleLM_K.H:57-101) and the port."""
+    g = golden_plm(mech)
+    rhoY, rhoH, T, mask = g["rrate/rhoY"], g["rrate/rhoH"], g["rrate/T"], g["rrate/mask"]
+    nc = T.size
+    R = capi.Reactor(mech, "ReactorCvode").init()
+    out = np.full_like(rhoY, -5.0)
+    Tin = T.copy()
+    R.reaction_rate_rhoY([0, 0, 0], [nc - 1, 0, 0], rhoY.copy(), rhoH.copy(), Tin, mask.copy(), out)
+    R.close()
+    assert np.array_equal(Tin, T)
+    m = mask < 0
+    assert m.any() and np.all(out[:, m] == 0.0)
+    ref = g["rrate/rhoYdot"]
+    err = np.abs(out - ref) / np.abs(ref).max(0, keepdims=True).clip(1e-300)
+    assert err[:, ~m].max() < 1e-9, err[:, ~m].max()
+    pr = port_lib.Port(mech).reaction_rate_rhoY(rhoY, rhoH, T, mask)
+    err = np.abs(out - pr) / np.abs(pr).max(0, keepdims=True).clip(1e-300)
+    assert err[:, ~m].max() < 1e-11, err[:, ~m].max()

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import MECHS, golden, check_state, scaled_err
+from conftest import MECHS, golden, golden_plm, check_state, scaled_err
 from golden.make_golden import CASES, DT
 
 
@@ -87,3 +87,33 @@ def test_port_knapsack_vs_reference(port_lib):
         assert sorted(map(sorted, pa.values())) == sorted(map(sorted, pb.values())), i
         i += 1
     assert i >= 8
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_port_reaction_rate_vs_reference(port_lib, mech):
+    """reactionRateRhoY (Source/PeleLM_K.H:57-101): port vs the reference's own inline function."""
+    g = golden_plm(mech)
+    P = port_lib.Port(mech)
+    got = P.reaction_rate_rhoY(g["rrate/rhoY"], g["rrate/rhoH"], g["rrate/T"], g["rrate/mask"])
+    ref = g["rrate/rhoYdot"]
+    m = g["rrate/mask"] < 0
+    assert m.any() and np.all(got[:, m] == 0.0) and np.all(ref[:, m] == 0.0)
+    err = np.abs(got - ref) / np.abs(ref).max(0, keepdims=True).clip(1e-300)
+    assert err[:, ~m].max() < 1e-9, err[:, ~m].max()
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_port_advance_chemistry_vs_reference(port_lib, mech):
+    """advance_chemistry body (PeleLM.cpp:5736-5800) around the port's react vs around the reference's react."""
+    g = golden_plm(mech)
+    P = port_lib.Port(mech).init(rtol=1e-8, atol=1e-10, max_order=2)
+    ins = [g["advchem/in_" + k] for k in ("rhoY", "rhoH", "T", "frcY", "frcH", "mask")]
+    rhoY, rhoH, T, FC, IR = port_lib.advance_chemistry_soa(P, *ins, DT, nthreads=4)
+    small = mech != "dodecane_lu"
+    # MKS state: atol 1e-10 g/cm^3 = 1e-7 kg/m^3
+    check_state((rhoY, T, rhoH, FC), (g["advchem/rhoY"], g["advchem/T"], g["advchem/rhoH"], g["advchem/FC"]), 1e-7,
+                tag=mech + "/advchem", rtol=1e-6, fc_equal_min=0.9 if small else None, fc_rel=0.05 if small else 0.15)
+    # I_R is (new - old)/dt - F: compare as a rate, scaled by the largest rate of the cell
+    ref = g["advchem/IR"]
+    e = np.abs(IR - ref) / (1e-6 * np.abs(ref) + 1e-6 * np.abs(ref).max(0, keepdims=True) + 1e-7 / DT)
+    assert e.max() <= 1.0, e.max()
