@@ -412,7 +412,8 @@ def run_gpu_arm(a):
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(a.mech, {}).get("dram_bytes_per_launch")
+                per_cell = json.load(open(tp)).get(a.mech, {}).get("dram_bytes_per_cell")
+                traffic = per_cell * box_cells if per_cell else None  # one launch = one box
             except Exception:
                 traffic = None
         line = {
