@@ -326,7 +326,7 @@ def run_gpu_arm(a):
         gst, full, new_owner, eff = step()
         if w == 0 and N > 1 and not np.array_equal(new_owner, owner):
             for key in ("hS", "hF", "hmask"):
-                payload = {b: boxes[b][key].to(dev) for b in boxes}
+                payload = {b: boxes[b][key].to(dev) for b in boxes if owner[b] == rank}
                 moved = pd.redistribute(payload, owner, new_owner)
                 for b, t in moved.items():
                     boxes.setdefault(b, {"id": b})[key] = t.cpu().pin_memory()
@@ -412,8 +412,8 @@ def run_gpu_arm(a):
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                per_cell = json.load(open(tp)).get(a.mech, {}).get("dram_bytes_per_cell")
-                traffic = per_cell * box_cells if per_cell else None  # one launch = one box
+                dram_per_cell = json.load(open(tp)).get(a.mech, {}).get("dram_bytes_per_cell")
+                traffic = dram_per_cell * box_cells if dram_per_cell else None  # one launch = one box
             except Exception:
                 traffic = None
         line = {
