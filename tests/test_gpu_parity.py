@@ -297,3 +297,36 @@ def test_reaction_rate_rhoY_vs_reference_and_port(capi, port_lib, mech):
     pr = port_lib.Port(mech).reaction_rate_rhoY(rhoY, rhoH, T, mask)
     err = np.abs(out - pr) / np.abs(pr).max(0, keepdims=True).clip(1e-300)
     assert err[:, ~m].max() < 1e-11, err[:, ~m].max()
+
+
+def test_rk64_two_cells_per_warp_is_bit_identical(capi):
+    """PLM_RK64_DUAL=1 selects the two-cells-per-warp ReactorRK64 kernel (rhs_warp2: both right-hand sides at once):
+    every cell must come out with exactly the bits of the default one-cell-per-warp kernel, whoever it was paired with."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from pelelm_b200 import capi, synth\n"
+        "out = {}\n"
+        "for mech, nc in (('LiDryer', 301), ('drm19', 130)):\n"
+        "    b = synth.synthetic_batch(mech, nc, seed=17, forcing=True)\n"
+        "    R = capi.Reactor(mech, 'ReactorRK64').init(rtol=1e-10, atol=1e-10)\n"
+        "    a = [b['rY'].copy(), b['rYsrc'].copy(), b['T'].copy(), b['rE'].copy(), b['rEsrc'].copy(), np.zeros(nc)]\n"
+        "    st = R.react([0, 0, 0], [nc - 1, 0, 0], a[0], a[1], a[2], a[3], a[4], a[5], None, 1e-5)\n"
+        "    R.close()\n"
+        "    out[mech + '_rY'], out[mech + '_T'], out[mech + '_rE'], out[mech + '_FC'] = a[0], a[2], a[3], a[5]\n"
+        "    out[mech + '_nfe'] = np.array(st['nfe'])\n"
+        "np.savez(sys.argv[1], **out)\n") % ROOT
+    res = []
+    with tempfile.TemporaryDirectory() as d:
+        for dual in ("0", "1"):
+            path = os.path.join(d, "o%s.npz" % dual)
+            env = dict(os.environ, PLM_RK64_DUAL=dual)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
+            res.append(dict(np.load(path)))
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k], equal_nan=True), k
+    assert res[0]["LiDryer_FC"].min() > 0
