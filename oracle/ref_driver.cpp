@@ -12,11 +12,15 @@
 //   cvode::cJac                               PelePhysics/Reactions/ReactorCvodeJacobian.cpp:84-153
 //   CKWC / GET_T_GIVEN_HY / CKHMS / CKCPBS    Support/Mechanism/Models/<mech>/mechanism.H
 //   reactionRateRhoY                          Source/PeleLM_K.H:57-101 (the reference's own inline function)
+//   VisMF::Write / VisMF::Read                amrex/Src/Base/AMReX_VisMF.cpp (the chkfile format ReactEval reads,
+//                                             PelePhysics/Testing/Exec/ReactEval/main.cpp:358-371)
 #include <AMReX.H>
 #include <AMReX_ParmParse.H>
 #include <AMReX_Box.H>
 #include <AMReX_Array4.H>
 #include <AMReX_Sundials.H>
+#include <AMReX_MultiFab.H>
+#include <AMReX_VisMF.H>
 
 #include "mechanism.H"
 #include "PelePhysics.H"
@@ -219,6 +223,49 @@ void ref_pty2rh(int ncells, double p, const double* T, const double* Y, double* 
     eos.PYT2R(p, Yl, T[c], rho[c]);
     eos.TY2H(T[c], Yl, h[c]);
   }
+}
+
+// VisMF::Write of a MultiFab made of nboxes boxes of side^3 cells laid along x, ncomp components, filled from
+// data [box][comp][k][j][i] (FAB order).
+int ref_vismf_write(const char* prefix, int nboxes, int side, int ncomp, const double* data)
+{
+  ref_setup();
+  amrex::BoxList bl;
+  for (int b = 0; b < nboxes; ++b)
+    bl.push_back(amrex::Box(amrex::IntVect(b * side, 0, 0), amrex::IntVect((b + 1) * side - 1, side - 1, side - 1)));
+  amrex::BoxArray ba(bl);
+  amrex::DistributionMapping dm(ba);
+  amrex::MultiFab mf(ba, dm, ncomp, 0);
+  const size_t per_box = size_t(side) * side * side * ncomp;
+  for (amrex::MFIter mfi(mf); mfi.isValid(); ++mfi)
+    std::memcpy(mf[mfi].dataPtr(), data + size_t(mfi.index()) * per_box, per_box * sizeof(double));
+  amrex::VisMF::Write(mf, prefix);
+  return 0;
+}
+
+// VisMF::Read: meta = {nboxes, ncomp, then lo[3] hi[3] per box}; out = the FABs back to back. Returns doubles written.
+long ref_vismf_read(const char* prefix, long max_doubles, double* out, int* meta, int max_meta)
+{
+  ref_setup();
+  amrex::MultiFab mf;
+  amrex::VisMF::Read(mf, prefix);
+  const int nb = static_cast<int>(mf.boxArray().size());
+  if (2 + 6 * nb > max_meta) return -1;
+  meta[0] = nb;
+  meta[1] = mf.nComp();
+  long off = 0;
+  for (int b = 0; b < nb; ++b) {
+    const amrex::Box& bx = mf.boxArray()[b];
+    for (int d = 0; d < 3; ++d) {
+      meta[2 + 6 * b + d] = bx.smallEnd(d);
+      meta[2 + 6 * b + 3 + d] = bx.bigEnd(d);
+    }
+    const long cnt = bx.numPts() * mf.nComp();
+    if (off + cnt > max_doubles) return -1;
+    std::memcpy(out + off, mf[b].dataPtr(), cnt * sizeof(double));
+    off += cnt;
+  }
+  return off;
 }
 
 void ref_species_names(char* buf, int buflen)

@@ -138,12 +138,34 @@ def knap():
     print("knapsack golden written")
 
 
+def vismf():
+    """tests/golden/vismf/: a MultiFab written by the reference's own VisMF::Write (amrex/Src/Base/AMReX_VisMF.cpp) through
+    oracle/ref_driver.cpp::ref_vismf_write, plus the values it holds -- pins pelelm_b200/vismf.py's reader to the format."""
+    import ctypes as C
+    import shutil
+    from oracle.pyoracle import Ref
+    R = Ref("LiDryer")
+    nb, side, nc = 3, 4, 5
+    rng = np.random.default_rng(11)
+    data = rng.normal(size=(nb, nc, side, side, side)) * 10.0 ** rng.integers(-12, 6, size=(nb, nc, 1, 1, 1))
+    d = os.path.join(HERE, "vismf")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(os.path.join(d, "Level_0"))
+    R.L.ref_vismf_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    R.L.ref_vismf_write(os.path.join(d, "Level_0", "OldState").encode(), nb, side, nc, data.ctypes.data)
+    np.save(os.path.join(d, "values.npy"), data)
+    print("vismf golden written:", sorted(os.listdir(os.path.join(d, "Level_0"))))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 2 and sys.argv[1] == "extra":
+    if len(sys.argv) > 1 and sys.argv[1] == "vismf":
+        vismf()
+    elif len(sys.argv) > 2 and sys.argv[1] == "extra":
         extra(sys.argv[2])
     elif len(sys.argv) > 1 and sys.argv[1] == "extra":  # only the PeleLM-side fixtures (the others stay as committed)
         for m in NCELLS:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "extra", m])
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "vismf"])
     elif len(sys.argv) > 1:
         knap() if sys.argv[1] == "knapsack" else one(sys.argv[1])
     else:
@@ -151,3 +173,5 @@ if __name__ == "__main__":
             subprocess.check_call([sys.executable, os.path.abspath(__file__), m])
         for m in NCELLS:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "extra", m])
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "vismf"])
+
