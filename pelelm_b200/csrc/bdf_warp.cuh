@@ -133,6 +133,29 @@ __device__ __noinline__ int gjinv_warp()
     }
     __syncwarp();
     const double* rk = A + k * ld;
+    if (NSLOT == 2 && L::PAIRS) {
+      // both rows of the lane in one sweep: the pivot row is read once for the two, and the two updates are independent
+      // chains (the inverse is 26 % of the dodecane_lu kernel, stalled on shared-memory latency)
+      const int i1 = lane + 32;
+      const bool on0 = lane != k, on1 = (i1 != k) && (i1 < n);
+      double2* r0 = reinterpret_cast<double2*>(A + lane * ld);
+      double2* r1 = reinterpret_cast<double2*>(A + (i1 < n ? i1 : n - 1) * ld);
+      const double f0 = on0 ? A[lane * ld + k] : 0.0, f1 = on1 ? A[i1 * ld + k] : 0.0;
+      if (on0) A[lane * ld + k] = 0.0;
+      if (on1) A[i1 * ld + k] = 0.0;
+      const double2* rk2 = reinterpret_cast<const double2*>(rk);
+#pragma unroll 3
+      for (int j = 0; j < n / 2; ++j) {
+        const double2 p = rk2[j];
+        double2 a = r0[j], b = r1[j];
+        a.x -= p.x * f0;
+        a.y -= p.y * f0;
+        b.x -= p.x * f1;
+        b.y -= p.y * f1;
+        if (on0) r0[j] = a;
+        if (on1) r1[j] = b;
+      }
+    } else
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       const int i = lane + 32 * s;
@@ -176,6 +199,22 @@ __device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::
   for (int s = 0; s < NSLOT; ++s) wb[L::YB + lane + 32 * s] = t[s];  // YB is free between right-hand-side calls
   __syncwarp();
   const double* pb = wb + L::YB;
+  if (NSLOT == 2 && L::PAIRS) {  // both rows of the lane against one pass over the right-hand side: four independent chains
+    const double2* r0 = reinterpret_cast<const double2*>(wb + L::A + lane * ld);
+    const double2* r1 = reinterpret_cast<const double2*>(wb + L::A + min(lane + 32, n - 1) * ld);
+    const double2* pb2 = reinterpret_cast<const double2*>(pb);
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 3
+    for (int j = 0; j < n / 2; ++j) {
+      const double2 b = pb2[j], u = r0[j], v = r1[j];
+      a0 = fma(u.x, b.x, a0);
+      a1 = fma(u.y, b.y, a1);
+      b0 = fma(v.x, b.x, b0);
+      b1 = fma(v.y, b.y, b1);
+    }
+    x[0] = a0 + a1;
+    x[NSLOT - 1] = b0 + b1;
+  } else
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s) {
     const double* row = wb + L::A + min(lane + 32 * s, n - 1) * ld;
@@ -362,12 +401,12 @@ struct BdfWarp {
       } else {
         dq_jac(A);
       }
-      for (int e = lane; e < n * ld; e += 32) Jsave[e] = A[e];
+      for (int e = lane; e < n * ld; e += 32) __stcs(Jsave + e, A[e]);  // streaming: keep the L1 for the mechanism tables
       nje++;
       nstlj = nst;
     } else {
       jcur = 0;
-      for (int e = lane; e < n * ld; e += 32) A[e] = Jsave[e];
+      for (int e = lane; e < n * ld; e += 32) A[e] = __ldcs(Jsave + e);
     }
     __syncwarp();
     const double c = -gamma;
