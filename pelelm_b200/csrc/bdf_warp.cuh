@@ -401,12 +401,17 @@ struct BdfWarp {
       } else {
         dq_jac(A);
       }
-      for (int e = lane; e < n * ld; e += 32) __stcs(Jsave + e, A[e]);  // streaming: keep the L1 for the mechanism tables
+      // large mechanisms: streaming stores / loads, the small L1 left beside 190 KB of shared memory stays with the
+      // mechanism tables (dodecane_lu +5 %); small ones keep the saved Jacobian L1 resident (drm19 -4 % if streamed)
+      for (int e = lane; e < n * ld; e += 32) {
+        if (L::BIG) __stcs(Jsave + e, A[e]);
+        else Jsave[e] = A[e];
+      }
       nje++;
       nstlj = nst;
     } else {
       jcur = 0;
-      for (int e = lane; e < n * ld; e += 32) A[e] = __ldcs(Jsave + e);
+      for (int e = lane; e < n * ld; e += 32) A[e] = L::BIG ? __ldcs(Jsave + e) : Jsave[e];
     }
     __syncwarp();
     const double c = -gamma;
