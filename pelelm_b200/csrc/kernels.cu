@@ -98,6 +98,22 @@ __device__ __forceinline__ double* block_prologue(const DevMech* __restrict__ dm
   }
   const int lane = threadIdx.x & 31;
   if (lane == 0) *slot_word() = 0;
+  if constexpr (L::TSM) {  // stage the tables of the right-hand side behind the warp areas (once per CTA)
+    __syncthreads();
+    const DevMech& m = smem_mech();
+    double* tb = const_cast<double*>(Tab<L>::base());
+    auto stage = [&](int off, const void* src, int ndoubles) {
+      const double* sp = static_cast<const double*>(src);
+      for (int i = threadIdx.x; i < ndoubles; i += blockDim.x) tb[off + i] = sp[i];
+    };
+    using T = Tab<L>;
+    stage(T::IMW, m.imw, L::NP); stage(T::MW, m.mw, L::NP); stage(T::TMID, m.tmid, L::NP);
+    stage(T::H, m.h, 12 * L::NP); stage(T::CP, m.cp, 10 * L::NP); stage(T::G, m.g, 14 * L::NP);
+    stage(T::RP0, m.rp0, 2 * L::NRP); stage(T::RP1, m.rp1, 2 * L::NRP);
+    stage(T::FO0, m.fo0, 64); stage(T::FO1, m.fo1, 64); stage(T::FO2, m.fo2, 64); stage(T::FO3, m.fo3, 64);
+    stage(T::FO4, m.fo4, 32); stage(T::SEG, m.seg, (kMaxSeg * L::NP) / 2);
+    stage(T::EFF, m.eff, m.emax * 64); stage(T::EFF + m.emax * 64, m.gat, m.glen * L::NP);
+  }
   for (int sl = 0; sl < L::SLOTS; ++sl) {
     double* w = warp_slot<L>(sl);
     for (int e = lane; e < L::TOTAL; e += 32) w[e] = 0.0;
@@ -588,7 +604,7 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
 }
 
 template <class L>
-__global__ void __launch_bounds__(kReactThreads) rhs_kernel(const DevMech* __restrict__ dm, int ncells, double t,
+__global__ void __launch_bounds__(L::WARPS * 32) rhs_kernel(const DevMech* __restrict__ dm, int ncells, double t,
                                                             const double* __restrict__ y,
                                                             const double* __restrict__ rhoe,
                                                             const double* __restrict__ rhoesrc,
@@ -619,7 +635,7 @@ __global__ void __launch_bounds__(kReactThreads) rhs_kernel(const DevMech* __res
 }
 
 template <class L>
-__global__ void __launch_bounds__(kReactThreads) jac_kernel(const DevMech* __restrict__ dm, int ncells,
+__global__ void __launch_bounds__(L::WARPS * 32) jac_kernel(const DevMech* __restrict__ dm, int ncells,
                                                             const double* __restrict__ y, double* __restrict__ Jout)
 {
   constexpr int NSLOT = L::NSLOT, n = L::N, ld = L::LD;
@@ -645,7 +661,7 @@ __global__ void __launch_bounds__(kReactThreads) jac_kernel(const DevMech* __res
 // PeleLM_K.H:57-101 reactionRateRhoY, one warp per cell: rho = sum rhoY (MKS), Y, T <- HY2T(rhoH/rho * 1e4, Y; guess T),
 // wdot*W = RTY2WDOT(rho * 1e-3, T, Y) (Fuego.H:168-183: C_k = rho Y_k / W_k, CKWC, x W_k), rhoYdot = x 1000.
 template <class L>
-__global__ void __launch_bounds__(kReactThreads) reaction_rate_kernel(const DevMech* __restrict__ dm, const BoxArgs a,
+__global__ void __launch_bounds__(L::WARPS * 32) reaction_rate_kernel(const DevMech* __restrict__ dm, const BoxArgs a,
                                                                       const plm_a4d out)
 {
   constexpr int NSLOT = L::NSLOT, ns = L::NS;
@@ -696,7 +712,7 @@ __global__ void __launch_bounds__(kReactThreads) reaction_rate_kernel(const DevM
       const int k = lane + 32 * s;
       if (k < ns) {
         const double cc = ((rho * Y[s]) * imw[s]) * 1.0e6;  // CKYTCR (mechanism.H:2403) then CKWC's SI conversion (:4911)
-        cg[k] = make_double2(cc, gibbs_k<L::NP>(m, k, T, logT, invT));
+        cg[k] = make_double2(cc, gibbs_k<L>(m, k, T, logT, invT));
         cpart += cc;
       }
     }
@@ -795,20 +811,28 @@ static cudaError_t dispatch(const DevMech& m, int integ, int qmax, F&& f)
   return cudaErrorInvalidValue;
 }
 
+// dynamic shared memory of every kernel instantiated on layout L: header + warp areas + (TSM) the staged tables
+template <class L>
+static size_t smem_bytes_of(const DevMech& m)
+{
+  return (size_t(kHdr) + size_t(L::WARPS) * L::SLOTS * L::TOTAL + size_t(Tab<L>::doubles(m.emax, m.glen))) * sizeof(double);
+}
+
 struct SmemQuery {
-  int wpb;
+  const DevMech* mech;
   size_t* out;
   template <class L, int IG>
   cudaError_t run()
   {
-    *out = (size_t(kHdr) + size_t(wpb) * L::SLOTS * L::TOTAL) * sizeof(double);
+    *out = smem_bytes_of<L>(*mech);
     return cudaSuccess;
   }
 };
 size_t react_smem_bytes(const DevMech& m, int integ, int qmax, int warps_per_block)
 {
   size_t v = 0;
-  SmemQuery q{warps_per_block, &v};
+  (void)warps_per_block;
+  SmemQuery q{&m, &v};
   dispatch(m, integ, qmax, q);
   return v;
 }
@@ -909,6 +933,7 @@ cudaError_t launch_react(const DevMech& m, const DevMech* dm, const ReactOpts& o
 }
 
 struct RhsLaunch {
+  const DevMech* mech;  // host copy (sizes)
   const DevMech* dm;
   int ncells;
   double t;
@@ -918,23 +943,24 @@ struct RhsLaunch {
   template <class L, int IG>
   cudaError_t run()
   {
-    const int wpb = kReactThreads / 32;
-    const size_t smem = (size_t(kHdr) + size_t(wpb) * L::TOTAL) * sizeof(double);
+    const int wpb = L::WARPS;
+    const size_t smem = smem_bytes_of<L>(*mech);
     const int blocks = std::max(1, std::min((ncells + wpb - 1) / wpb, 148 * 4));
     cudaError_t e = cudaFuncSetAttribute(rhs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    rhs_kernel<L><<<blocks, kReactThreads, smem, stream>>>(dm, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot);
+    rhs_kernel<L><<<blocks, L::WARPS * 32, smem, stream>>>(dm, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot);
     return cudaGetLastError();
   }
 };
 cudaError_t launch_rhs(const DevMech& m, const DevMech* dm, int ncells, double t, const double* y, const double* rhoe,
                        const double* rhoesrc, const double* rYsrc, double* ydot, cudaStream_t stream)
 {
-  RhsLaunch l{dm, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot, stream};
+  RhsLaunch l{&m, dm, ncells, t, y, rhoe, rhoesrc, rYsrc, ydot, stream};
   return dispatch(m, kIntegCvode, 2, l);
 }
 
 struct JacLaunch {
+  const DevMech* mech;
   const DevMech* dm;
   int ncells;
   const double* y;
@@ -943,22 +969,23 @@ struct JacLaunch {
   template <class L, int IG>
   cudaError_t run()
   {
-    const int wpb = kReactThreads / 32;
-    const size_t smem = (size_t(kHdr) + size_t(wpb) * L::TOTAL) * sizeof(double);
+    const int wpb = L::WARPS;
+    const size_t smem = smem_bytes_of<L>(*mech);
     const int blocks = std::max(1, std::min((ncells + wpb - 1) / wpb, 148 * 4));
     cudaError_t e = cudaFuncSetAttribute(jac_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    jac_kernel<L><<<blocks, kReactThreads, smem, stream>>>(dm, ncells, y, J);
+    jac_kernel<L><<<blocks, L::WARPS * 32, smem, stream>>>(dm, ncells, y, J);
     return cudaGetLastError();
   }
 };
 cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const double* y, double* J, cudaStream_t stream)
 {
-  JacLaunch l{dm, ncells, y, J, stream};
+  JacLaunch l{&m, dm, ncells, y, J, stream};
   return dispatch(m, kIntegCvode, 2, l);
 }
 
 struct RateLaunch {
+  const DevMech* mech;
   const DevMech* dm;
   const BoxArgs& a;
   plm_a4d out;
@@ -966,19 +993,19 @@ struct RateLaunch {
   template <class L, int IG>
   cudaError_t run()
   {
-    const int wpb = kReactThreads / 32;
-    const size_t smem = (size_t(kHdr) + size_t(wpb) * L::TOTAL) * sizeof(double);
+    const int wpb = L::WARPS;
+    const size_t smem = smem_bytes_of<L>(*mech);
     const int64_t want = (a.ncells + wpb - 1) / wpb;
     const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8)));
     cudaError_t e = cudaFuncSetAttribute(reaction_rate_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    reaction_rate_kernel<L><<<blocks, kReactThreads, smem, stream>>>(dm, a, out);
+    reaction_rate_kernel<L><<<blocks, L::WARPS * 32, smem, stream>>>(dm, a, out);
     return cudaGetLastError();
   }
 };
 cudaError_t launch_reaction_rate(const DevMech& m, const DevMech* dm, const BoxArgs& a, plm_a4d rhoYdot, cudaStream_t stream)
 {
-  RateLaunch l{dm, a, rhoYdot, stream};
+  RateLaunch l{&m, dm, a, rhoYdot, stream};
   return dispatch(m, kIntegCvode, 2, l);
 }
 

@@ -330,3 +330,26 @@ def test_rk64_two_cells_per_warp_is_bit_identical(capi):
     for k in res[0]:
         assert np.array_equal(res[0][k], res[1][k], equal_nan=True), k
     assert res[0]["LiDryer_FC"].min() > 0
+
+
+@pytest.mark.parametrize("mech,integ", [("drm19", "ReactorCvode"), ("LiDryer", "ReactorRK64")])
+def test_subcycled_calls_with_advancing_time(capi, port_lib, mech, integ):
+    """ReactEval's loop (PelePhysics/Testing/Exec/ReactEval/main.cpp:520-560, `ode.ndt` sub-steps): react() called
+    repeatedly on its own output with time = 0, dt, 2 dt (the forcing term of fKernelSpec uses t - time_init)."""
+    from pelelm_b200 import synth
+    nc, ndt = 96, 3
+    b = synth.synthetic_batch(mech, nc, seed=77, forcing=True, t_range=(900.0, 1400.0) if integ == "ReactorRK64" else (900.0, 2600.0))
+    ikw = dict(rtol=1e-9, atol=1e-10, max_order=2)
+    P = port_lib.Port(mech).init(integrator=integ, **ikw)
+    R = capi.Reactor(mech, integ).init(**ikw)
+    g = [b["rY"].copy(), b["rYsrc"].copy(), b["T"].copy(), b["rE"].copy(), b["rEsrc"].copy(), np.zeros(nc)]
+    p = [b["rY"].copy(), b["T"].copy(), b["rE"].copy()]
+    mask = np.ones(nc, dtype=np.int32)
+    for k in range(ndt):
+        t = k * DT
+        R.react([0, 0, 0], [nc - 1, 0, 0], g[0], g[1], g[2], g[3], g[4], g[5], mask, DT, time=t)
+        rY, T, rE, FC = P.react_soa(p[0], b["rYsrc"], p[1], p[2], b["rEsrc"], mask, DT, time=t, nthreads=4)
+        p = [rY, T, rE]
+        check_state((g[0], g[2], g[3], g[5]), (rY, T, rE, FC), 1e-10, tag="%s step %d" % (mech, k), rtol=2e-6, fc_rel=0.05)
+    R.close()
+    assert np.array_equal(g[3], p[2])  # rhoH: in + dt*src three times, bit-exact
