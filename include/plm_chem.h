@@ -43,7 +43,8 @@ int  plm_reactor_create(plm_reactor** out, const char* mechanism, const char* in
 
 /* ReactorBase::init(reactor_type, ncells) + the ParmParse keys it reads
  * (ReactorCvode.cpp:9-31 ode.{rtol,atol,max_nls_iters,clean_init_massfrac}, :722-726 cvode.{solve_type,max_order};
- * ReactorRK64.cpp:14-20 ode.rk64_nsubsteps_{guess,min,max}).  reactor_type: 2 = h (HP; PeleLM). 1 (e) is not built.
+ * ReactorRK64.cpp:14-20 ode.rk64_nsubsteps_{guess,min,max}).  reactor_type: 1 = internal energy (UV; REY2T / Ei / Cv, consP = 0 in cJac; the ReactEval default),
+ * 2 = enthalpy (HP; PeleLM).
  * solve_type: "denseAJ_direct" (analytic Jacobian) | "dense_direct" (difference-quotient Jacobian). */
 int  plm_reactor_init(plm_reactor*, int reactor_type, double rtol, double atol, int max_order, int max_nls_iters,
                       int clean_init_massfrac, const char* solve_type, int rk64_guess, int rk64_min, int rk64_max);

@@ -65,6 +65,7 @@ enum { NLS_SUCCESS = 0, NLS_CONTINUE = 901, NLS_CONV_RECVR = 902 };
 typedef struct {
   const plm_mech_tables* m;
   int n, qmax, maxcor, maxnef, mxstep, msbj, ajac;
+  int rt; /* ode.reactor_type */
   double rtol, atolv[ORC_MAXN];
   double rhoe_init, rhoesrc;
   const double* rYsrc;
@@ -109,7 +110,7 @@ static int ewtset(cvmem* cv, const double* ycur, double* w)
 }
 static void f(cvmem* cv, double t, const double* y, double* ydot)
 {
-  orc_rhs(cv->m, t, y, ydot, cv->rhoe_init, cv->rhoesrc, cv->rYsrc);
+  orc_rhs_rt(cv->m, cv->rt, t, y, ydot, cv->rhoe_init, cv->rhoesrc, cv->rYsrc);
   cv->nfe++;
 }
 
@@ -177,7 +178,7 @@ static void dq_jac(cvmem* cv, double t, double* y, const double* fy, double* J)
     double inc = srur * fabs(yjsaved);
     if (minInc / cv->ewt[j] > inc) inc = minInc / cv->ewt[j];
     y[j] += inc;
-    orc_rhs(cv->m, t, y, ft, cv->rhoe_init, cv->rhoesrc, cv->rYsrc);
+    orc_rhs_rt(cv->m, cv->rt, t, y, ft, cv->rhoe_init, cv->rhoesrc, cv->rYsrc);
     cv->nfe++; /* counted as nfeLS by CVODE; PelePhysics adds both into FC */
     y[j] = yjsaved;
     const double inc_inv = ONE / inc;
@@ -197,7 +198,7 @@ static int lsetup(cvmem* cv)
     memcpy(cv->A, cv->savedJ, sizeof(double) * n * n);
   } else {
     cv->jcur = 1;
-    if (cv->ajac) orc_cjac(cv->m, cv->y, cv->A);
+    if (cv->ajac) orc_cjac_rt(cv->m, cv->rt, cv->y, cv->A);
     else dq_jac(cv, cv->tn, cv->y, cv->ftemp, cv->A);
     memcpy(cv->savedJ, cv->A, sizeof(double) * n * n);
   }
@@ -669,6 +670,7 @@ int orc_cvode_cell(const plm_mech_tables* m, const orc_opts* o, double* yio, dou
   cv->mxstep = 10000;
   cv->msbj = 100;
   cv->ajac = o->analytical_jacobian;
+  cv->rt = o->reactor_type;
   cv->rtol = o->rtol;
   for (int i = 0; i < n; i++) cv->atolv[i] = (o->typ_vals[0] > 0.0) ? o->typ_vals[i] * o->atol : o->atol;
   cv->rhoe_init = rhoe_init;

@@ -60,6 +60,91 @@ void orc_dcp_R(const plm_mech_tables* m, double* s, const double* tc)
   }
 }
 
+/* cv_R, speciesInternalEnergy (LiDryer mechanism.H:115, :505): the cp_R / speciesEnthalpy polynomials with the constant term
+ * a0 - 1 (tables: a0m1) */
+void orc_cv_R(const plm_mech_tables* m, double* s, const double* tc)
+{
+  const double T = tc[1];
+  for (int k = 0; k < m->ns; ++k) {
+    const int rg = (T < m->tmid[k] ? 0 : 1);
+    const double* c = m->cp + (k * 2 + rg) * 5;
+    s[k] = m->a0m1[k * 2 + rg] + c[1] * tc[1] + c[2] * tc[2] + c[3] * tc[3] + c[4] * tc[4];
+  }
+}
+void orc_e_RT(const plm_mech_tables* m, double* s, const double* tc)
+{
+  const double T = tc[1], invT = 1 / T;
+  for (int k = 0; k < m->ns; ++k) {
+    const int rg = (T < m->tmid[k] ? 0 : 1);
+    const double* c = m->h + (k * 2 + rg) * 6;
+    s[k] = m->a0m1[k * 2 + rg] + c[1] * tc[1] + c[2] * tc[2] + c[3] * tc[3] + c[4] * tc[4] + c[5] * invT;
+  }
+}
+/* CKCVBS (LiDryer mechanism.H:835), CKUBMS :933, CKUMS :1708 */
+double orc_cvbs(const plm_mech_tables* m, double T, const double* y)
+{
+  const double tc[5] = {0, T, T * T, T * T * T, T * T * T * T};
+  double cvor[ORC_MAXS], result = 0;
+  orc_cv_R(m, cvor, tc);
+  for (int i = 0; i < m->ns; ++i) result += cvor[i] * y[i] * (1.0 / m->mw[i]);
+  return result * RU;
+}
+double orc_ubms(const plm_mech_tables* m, double T, const double* y)
+{
+  const double tc[5] = {0, T, T * T, T * T * T, T * T * T * T};
+  double ums[ORC_MAXS], result = 0;
+  const double RT = RU * T;
+  orc_e_RT(m, ums, tc);
+  for (int i = 0; i < m->ns; ++i) result += y[i] * ums[i] * (1.0 / m->mw[i]);
+  return result * RT;
+}
+void orc_ums(const plm_mech_tables* m, double T, double* ums)
+{
+  const double tc[5] = {0, T, T * T, T * T * T, T * T * T * T};
+  const double RT = RU * T;
+  orc_e_RT(m, ums, tc);
+  for (int i = 0; i < m->ns; ++i) ums[i] *= RT * (1.0 / m->mw[i]);
+}
+/* GET_T_GIVEN_EY (drm19 mechanism.H:1912-1963): same iteration as GET_T_GIVEN_HY on e(T), cv */
+int orc_get_T_given_eY(const plm_mech_tables* m, double ein, const double* y, double* t)
+{
+  const int maxiter = 200;
+  const double tol = 1.e-6;
+  double tmin = 90, tmax = 4000;
+  double e1, cv, t1, dt;
+  const double emin = orc_ubms(m, tmin, y);
+  const double emax = orc_ubms(m, tmax, y);
+  if (ein < emin) {
+    cv = orc_cvbs(m, tmin, y);
+    *t = tmin - (emin - ein) / cv;
+    return 1;
+  }
+  if (ein > emax) {
+    cv = orc_cvbs(m, tmax, y);
+    *t = tmax - (emax - ein) / cv;
+    return 1;
+  }
+  t1 = *t;
+  if (t1 < tmin || t1 > tmax) t1 = tmin + (tmax - tmin) / (emax - emin) * (ein - emin);
+  for (int i = 0; i < maxiter; ++i) {
+    e1 = orc_ubms(m, t1, y);
+    cv = orc_cvbs(m, t1, y);
+    dt = (ein - e1) / cv;
+    if (dt > 100.) {
+      dt = 100.;
+    } else if (dt < -100.) {
+      dt = -100.;
+    } else if (fabs(dt) < tol) {
+      break;
+    } else if (t1 + dt == t1) {
+      break;
+    }
+    t1 += dt;
+  }
+  *t = t1;
+  return 0;
+}
+
 /* CKCPBS :1605-1626 */
 double orc_cpbs(const plm_mech_tables* m, double T, const double* y)
 {
@@ -261,7 +346,7 @@ static int dphase(const double* sc, const int* idx, const double* nu, int a, int
 
 /* aJacobian :9696-14742 with consP = 1 (h-reactor; ReactorCvodeJacobian.cpp:129-131).
  * J column-major n x n, n = ns+1, J[col*n+row]; sc in mol/m^3. */
-void orc_ajacobian_consP(const plm_mech_tables* m, double* J, const double* sc, double T)
+void orc_ajacobian(const plm_mech_tables* m, double* J, const double* sc, double T, int consP)
 {
   const int ns = m->ns, n = ns + 1;
   double wdot[ORC_MAXS], g_RT[ORC_MAXS], h_RT[ORC_MAXS];
@@ -279,6 +364,8 @@ void orc_ajacobian_consP(const plm_mech_tables* m, double* J, const double* sc, 
   const double ln10 = log(10.0);
   const double log10e = 1.0 / log(10.0);
 
+  double dqdc_keep[ORC_MAXS];
+  for (int j = 0; j < ns; ++j) dqdc_keep[j] = 0.0;
   for (int r = 0; r < m->nr; ++r) {
     const int type = m->type[r];
     double alpha = 0.0;
@@ -361,33 +448,59 @@ void orc_ajacobian_consP(const plm_mech_tables* m, double* J, const double* sc, 
     /* columns: every species the rate depends on */
     for (int j = 0; j < ns; ++j) {
       double dqdci = 0.0, d;
-      int dep = 0;
+      int dep = 0, zero_eff = 0;
       if (type != 0) {
-        for (int s = m->eoff[r]; s < m->eoff[r + 1]; ++s)
-          if (m->eidx[s] == j) {
-            dqdci = (m->eval[s] - 1) * dcdc_fac;
-            dep = 1;
-          }
+        if (consP) {
+          for (int s = m->eoff[r]; s < m->eoff[r + 1]; ++s)
+            if (m->eidx[s] == j) {
+              dqdci = (m->eval[s] - 1) * dcdc_fac;
+              dep = 1;
+            }
+        } else { /* constant volume: every species is a third body (efficiency 1 unless listed), mechanism.H "else" branches */
+          dqdci = dcdc_fac;
+          for (int s = m->eoff[r]; s < m->eoff[r + 1]; ++s)
+            if (m->eidx[s] == j) {
+              dqdci = m->eval[s] * dcdc_fac;
+              zero_eff = (m->eval[s] == 0.0);
+            }
+          dep = 1;
+        }
       }
+      int phase_dep = 0;
       if (dphase(sc, m->ridx, m->rval, m->roff[r], m->roff[r + 1], j, &d)) {
         dqdci += k_f * d;
-        dep = 1;
+        dep = phase_dep = 1;
       }
       if (m->rev[r] && dphase(sc, m->pidx, m->pval, m->poff[r], m->poff[r + 1], j, &d)) {
         dqdci -= k_r * d;
-        dep = 1;
+        dep = phase_dep = 1;
       }
       if (!dep) continue;
+      if (type != 0 && !consP) {
+        /* The generated reference keeps ONE dqdc[] array for the whole routine and, in these branches, does not assign
+         * the entry of a species whose efficiency is 0 and that is neither reactant nor product (e.g. drm19
+         * mechanism.H reaction 22, dqdc[5] / dqdc[12]) -- yet adds all ns entries to J: such an entry still holds
+         * the value the previous third-body reaction left there. Reproduced, so that cJac matches entry by entry. */
+        if (zero_eff && !phase_dep) dqdci = dqdc_keep[j];
+        else dqdc_keep[j] = dqdci;
+      }
       for (int s = m->noff[r]; s < m->noff[r + 1]; ++s) J[j * n + m->nidx[s]] += m->nval[s] * dqdci;
     }
     for (int s = m->noff[r]; s < m->noff[r + 1]; ++s) J[ns * n + m->nidx[s]] += m->nval[s] * dqdT;
   }
 
   /* closure :14705-14741 */
-  double c_R[ORC_MAXS], dcRdT[ORC_MAXS];
-  orc_cp_R(m, c_R, tc);
-  orc_dcp_R(m, dcRdT, tc);
+  double c_R[ORC_MAXS], dcRdT[ORC_MAXS], e_RT[ORC_MAXS];
   const double* eh_RT = h_RT;
+  if (consP) {
+    orc_cp_R(m, c_R, tc);
+    orc_dcp_R(m, dcRdT, tc);
+  } else {
+    orc_cv_R(m, c_R, tc);
+    orc_dcp_R(m, dcRdT, tc);
+    orc_e_RT(m, e_RT, tc);
+    eh_RT = e_RT;
+  }
   double cmix = 0.0, ehmix = 0.0, dcmixdT = 0.0, dehmixdT = 0.0;
   for (int k = 0; k < ns; ++k) {
     cmix += c_R[k] * sc[k];
@@ -408,7 +521,9 @@ void orc_ajacobian_consP(const plm_mech_tables* m, double* J, const double* sc, 
 }
 
 /* DWDOT :14745-14765 + mass scaling of cJac (ReactorCvodeJacobian.cpp:101-148); y = [rhoY_k, T] */
-void orc_cjac(const plm_mech_tables* m, const double* y, double* Jout)
+void orc_cjac(const plm_mech_tables* m, const double* y, double* Jout) { orc_cjac_rt(m, 2, y, Jout); }
+/* cJac with the reactor type: consP = (reactor_type != eint) (ReactorCvodeJacobian.cpp:109-118) */
+void orc_cjac_rt(const plm_mech_tables* m, int reactor_type, const double* y, double* Jout)
 {
   const int ns = m->ns, n = ns + 1;
   double rho = 0.0, massfrac[ORC_MAXS], C[ORC_MAXS], c[ORC_MAXS];
@@ -418,7 +533,7 @@ void orc_cjac(const plm_mech_tables* m, const double* y, double* Jout)
   for (int i = 0; i < ns; ++i) massfrac[i] = y[i] / rho;
   for (int i = 0; i < ns; ++i) C[i] = rho * massfrac[i] * (1.0 / m->mw[i]); /* CKYTCR :2403 */
   for (int k = 0; k < ns; ++k) c[k] = 1.e6 * C[k];
-  orc_ajacobian_consP(m, Jt, c, temp);
+  orc_ajacobian(m, Jt, c, temp, reactor_type == 1 ? 0 : 1);
   for (int k = 0; k < ns; ++k) {
     Jt[ns * n + k] *= 1.e-6;
     Jt[k * n + ns] *= 1.e6;
@@ -440,6 +555,12 @@ void orc_cjac(const plm_mech_tables* m, const double* y, double* Jout)
 void orc_rhs(const plm_mech_tables* m, double dt_save, const double* y, double* ydot, double rhoe_init,
              double rhoesrc_ext, const double* rYs)
 {
+  orc_rhs_rt(m, 2, dt_save, y, ydot, rhoe_init, rhoesrc_ext, rYs);
+}
+/* reactor_type 1 = eint (REY2T, RTY2Ei, RTY2Cv), 2 = enthalpy (RHY2T, RTY2Hi, RTY2Cp): ReactorUtils.H:300-316 */
+void orc_rhs_rt(const plm_mech_tables* m, int reactor_type, double dt_save, const double* y, double* ydot, double rhoe_init,
+                double rhoesrc_ext, const double* rYs)
+{
   const int ns = m->ns;
   double massfrac[ORC_MAXS], ei[ORC_MAXS], cdots[ORC_MAXS], C[ORC_MAXS];
   double rho = 0.0;
@@ -451,9 +572,16 @@ void orc_rhs(const plm_mech_tables* m, double dt_save, const double* y, double* 
   for (int k = 0; k < ns; ++k) massfrac[k] *= rho_inv;
   const double nrg = (rhoe_init + rhoesrc_ext * dt_save) * rho_inv;
   double temp = y[ns];
-  orc_get_T_given_hY(m, nrg, massfrac, &temp);
-  orc_hms(m, temp, ei);
-  const double cp = orc_cpbs(m, temp, massfrac);
+  double cp;
+  if (reactor_type == 1) {
+    orc_get_T_given_eY(m, nrg, massfrac, &temp);
+    orc_ums(m, temp, ei);
+    cp = orc_cvbs(m, temp, massfrac);
+  } else {
+    orc_get_T_given_hY(m, nrg, massfrac, &temp);
+    orc_hms(m, temp, ei);
+    cp = orc_cpbs(m, temp, massfrac);
+  }
   for (int i = 0; i < ns; ++i) C[i] = rho * massfrac[i] * (1.0 / m->mw[i]);
   orc_ckwc(m, temp, C, cdots);
   for (int k = 0; k < ns; ++k) cdots[k] *= m->mw[k];

@@ -15,6 +15,7 @@ typedef struct plm_mech_tables {
   int n_troe, n_lind, n_3b, n_simple;
   const char* const* species;
   const double *mw, *tmid, *cp, *h, *g, *dcp;
+  const double* a0m1; /* [species][0=low,1=high]: constant term of cv/R and e/RT (= a0 - 1 in decimal) */
   const double *A, *b, *EaR, *A0, *b0, *Ea0R, *troe;
   const int *troe_np, *type, *rev;
   const double* dn;

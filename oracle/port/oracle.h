@@ -23,10 +23,17 @@ double orc_cpbs(const plm_mech_tables* m, double T, const double* y);
 double orc_hbms(const plm_mech_tables* m, double T, const double* y);
 void orc_hms(const plm_mech_tables* m, double T, double* hms);
 int orc_get_T_given_hY(const plm_mech_tables* m, double hin, const double* y, double* t);
+int orc_get_T_given_eY(const plm_mech_tables* m, double ein, const double* y, double* t);
+double orc_cvbs(const plm_mech_tables* m, double T, const double* y);
+double orc_ubms(const plm_mech_tables* m, double T, const double* y);
+void orc_ums(const plm_mech_tables* m, double T, double* ums);
 void orc_production_rate(const plm_mech_tables* m, double* wdot, const double* sc, double T);
 void orc_ckwc(const plm_mech_tables* m, double T, const double* C, double* wdot);
-void orc_ajacobian_consP(const plm_mech_tables* m, double* J, const double* sc, double T);
+void orc_ajacobian(const plm_mech_tables* m, double* J, const double* sc, double T, int consP);
 void orc_cjac(const plm_mech_tables* m, const double* y, double* Jout);
+void orc_cjac_rt(const plm_mech_tables* m, int reactor_type, const double* y, double* Jout);
+void orc_rhs_rt(const plm_mech_tables* m, int reactor_type, double dt_save, const double* y, double* ydot, double rhoe_init,
+                double rhoesrc_ext, const double* rYs);
 void orc_reaction_rate_rhoY(const plm_mech_tables* m, const double* rhoY, double rhoH, double T, int mask, double* rhoYdot);
 void orc_rhs(const plm_mech_tables* m, double dt_save, const double* y, double* ydot, double rhoe_init,
              double rhoesrc_ext, const double* rYs);
@@ -40,6 +47,7 @@ typedef struct orc_opts {
   int clean_init_massfrac;
   int rk64_guess, rk64_min, rk64_max;
   int analytical_jacobian;   /* 1: denseAJ_direct (cJac), 0: dense_direct (difference quotient) */
+  int reactor_type;          /* ode.reactor_type: 1 = internal energy (UV), 2 = enthalpy (HP; PeleLM) */
 } orc_opts;
 void orc_default_opts(orc_opts* o);
 

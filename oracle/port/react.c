@@ -22,6 +22,7 @@ void orc_default_opts(orc_opts* o)
   o->rk64_min = 5;
   o->rk64_max = 500;
   o->analytical_jacobian = 1;
+  o->reactor_type = 2;
 }
 
 static double dmin(double a, double b) { return a < b ? a : b; }
@@ -48,7 +49,8 @@ static double react_cell(const plm_mech_tables* m, const orc_opts* o, int use_rk
   for (int k = 0; k < ns; k++) massfrac[k] *= rho_inv;
   double temp = *T;
   const double rhoe_init = *rE;
-  orc_get_T_given_hY(m, rhoe_init * rho_inv, massfrac, &temp);
+  if (o->reactor_type == 1) orc_get_T_given_eY(m, rhoe_init * rho_inv, massfrac, &temp); /* REY2T, ReactorUtils.H:118-126 */
+  else orc_get_T_given_hY(m, rhoe_init * rho_inv, massfrac, &temp);
   y[ns] = temp;
   double fc;
   if (use_rk64) {
@@ -78,7 +80,8 @@ static double react_cell(const plm_mech_tables* m, const orc_opts* o, int use_rk
   for (int k = 0; k < ns; k++) massfrac[k] *= rho_inv;
   temp = y[ns];
   *rE = rhoe_init + dt * rEsrc;
-  orc_get_T_given_hY(m, (*rE) * rho_inv, massfrac, &temp);
+  if (o->reactor_type == 1) orc_get_T_given_eY(m, (*rE) * rho_inv, massfrac, &temp);
+  else orc_get_T_given_hY(m, (*rE) * rho_inv, massfrac, &temp);
   *T = temp;
   return fc;
 }

@@ -28,7 +28,7 @@ int orc_rk64_cell(const plm_mech_tables* m, const orc_opts* o, double* soln, dou
   while (current_time < time_out) {
     for (int i = 0; i < neq; i++) err[i] = 0.0;
     for (int stage = 0; stage < 6; stage++) {
-      orc_rhs(m, current_time - time_init, soln, rhs, rhoe_init, rhoesrc_ext, rYsrc);
+      orc_rhs_rt(m, o->reactor_type, current_time - time_init, soln, rhs, rhoe_init, rhoesrc_ext, rYsrc);
       for (int i = 0; i < neq; i++) {
         err[i] += err_rk64[stage] * dt_rk * rhs[i];
         soln[i] = carry[i] + alpha_rk64[stage] * dt_rk * rhs[i];

@@ -49,7 +49,7 @@ class Opts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("typ_vals", C.c_double * MAXN),
                 ("max_order", C.c_int), ("max_nls_iters", C.c_int), ("clean_init_massfrac", C.c_int),
                 ("rk64_guess", C.c_int), ("rk64_min", C.c_int), ("rk64_max", C.c_int),
-                ("analytical_jacobian", C.c_int)]
+                ("analytical_jacobian", C.c_int), ("reactor_type", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -116,17 +116,17 @@ class Ref:
         self.L.ref_reaction_rate_rhoY(nc, 1, 1, _p(rhoY), _p(rhoH), _p(T), _pi(mask), _p(out))
         return out
 
-    def rhs(self, y, rhoe, rhoesrc, rYsrc, t=0.0):
+    def rhs(self, y, rhoe, rhoesrc, rYsrc, t=0.0, reactor_type=2):
         nc = y.shape[0]
         out = np.zeros_like(y)
-        self.L.ref_rhs(nc, 2, t, _p(y), _p(rhoe), _p(rhoesrc), _p(rYsrc), _p(out))
+        self.L.ref_rhs(nc, reactor_type, t, _p(y), _p(rhoe), _p(rhoesrc), _p(rYsrc), _p(out))
         return out
 
-    def jac(self, y):
+    def jac(self, y, reactor_type=2):
         nc = y.shape[0]
         J = np.zeros((nc, self.n * self.n))
         self.L.ref_setup()
-        self.L.ref_jac(nc, 2, _p(y), _p(J))
+        self.L.ref_jac(nc, reactor_type, _p(y), _p(J))
         return J
 
     def ckwc(self, T, Cc):
@@ -207,8 +207,9 @@ class Port:
 
     def init(self, integrator="ReactorCvode", solve_type="denseAJ_direct", rtol=1e-10, atol=1e-10, max_order=2,
              max_nls_iters=3, clean_init_massfrac=0, rk64=(10, 5, 500), reactor_type=2):
-        assert reactor_type == 2
+        assert reactor_type in (1, 2)
         o = self.opts
+        o.reactor_type = reactor_type
         o.rtol, o.atol, o.max_order, o.max_nls_iters = rtol, atol, max_order, max_nls_iters
         o.clean_init_massfrac = clean_init_massfrac
         o.rk64_guess, o.rk64_min, o.rk64_max = rk64
@@ -244,16 +245,18 @@ class Port:
             out[:, c] = col
         return out
 
-    def rhs(self, y, rhoe, rhoesrc, rYsrc, t=0.0):
+    def rhs(self, y, rhoe, rhoesrc, rYsrc, t=0.0, reactor_type=2):
         out = np.zeros_like(y)
+        self.L.orc_rhs_rt.argtypes = [C.c_void_p, C.c_int, C.c_double, c_dp, c_dp, C.c_double, C.c_double, c_dp]
         for c in range(y.shape[0]):
-            self.L.orc_rhs(self.m, t, _p(y[c]), _p(out[c]), rhoe[c], rhoesrc[c], _p(rYsrc[c]))
+            self.L.orc_rhs_rt(self.m, reactor_type, t, _p(y[c]), _p(out[c]), rhoe[c], rhoesrc[c], _p(rYsrc[c]))
         return out
 
-    def jac(self, y):
+    def jac(self, y, reactor_type=2):
         J = np.zeros((y.shape[0], self.n * self.n))
+        self.L.orc_cjac_rt.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp]
         for c in range(y.shape[0]):
-            self.L.orc_cjac(self.m, _p(y[c]), _p(J[c]))
+            self.L.orc_cjac_rt(self.m, reactor_type, _p(y[c]), _p(J[c]))
         return J
 
     def ckwc(self, T, Cc):

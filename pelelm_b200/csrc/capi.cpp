@@ -87,6 +87,7 @@ struct plm_reactor {
   plm::DevMechOwner mech;
   int integ = plm::kIntegCvode;
   bool inited = false;
+  int reactor_type = 2;
   plm::ReactOpts opts{};
   int num_sms = 0;
   DevBuf ctrl;     // [kSlots] work-queue counters, then kStatWords cumulative statistics (unsigned long long)
@@ -165,8 +166,8 @@ int plm_reactor_init(plm_reactor* r, int reactor_type, double rtol, double atol,
                      int clean_init_massfrac, const char* solve_type, int rk64_guess, int rk64_min, int rk64_max)
 {
   if (!r) return fail(PLM_ERR_ARG, "null reactor");
-  if (reactor_type != 2)  // ReactorTypes.H:15-21 accepts 1|2; only the h (HP) reactor PeleLM uses is built
-    return fail(PLM_ERR_ARG, "only reactor_type 2 (h, constant pressure) is implemented");
+  if (reactor_type != 1 && reactor_type != 2)  // ReactorTypes.H:15-21: 1 = internal energy (UV), 2 = enthalpy (HP; PeleLM)
+    return fail(PLM_ERR_ARG, "reactor_type must be 1 (internal energy) or 2 (enthalpy)");
   if (!(rtol > 0) || !(atol > 0)) return fail(PLM_ERR_ARG, "rtol/atol must be positive");
   if (max_order < 1 || max_order > 5) return fail(PLM_ERR_ARG, "cvode.max_order must be in 1..5");
   if (max_nls_iters < 1) return fail(PLM_ERR_ARG, "ode.max_nls_iters must be >= 1");
@@ -188,6 +189,8 @@ int plm_reactor_init(plm_reactor* r, int reactor_type, double rtol, double atol,
   o.rk64_min = rk64_min;
   o.rk64_max = rk64_max;
   o.use_typ = had_typ;
+  if (plm::select_reactor_type(&r->mech, reactor_type) != 0) return fail(PLM_ERR_CUDA, "could not update the mechanism descriptor");
+  r->reactor_type = reactor_type;
   r->inited = true;
   r->cfg_qmax = -1;
   return PLM_OK;
@@ -396,6 +399,7 @@ int plm_reaction_rate_rhoY(plm_reactor* r, const int lo[3], const int hi[3], plm
 {
   if (!r || !lo || !hi) return fail(PLM_ERR_ARG, "null argument");
   if (!rhoY.p || !rhoH.p || !T.p || !rhoYdot.p) return fail(PLM_ERR_ARG, "null array");
+  if (r->reactor_type != 2) return fail(PLM_ERR_ARG, "reactionRateRhoY works on enthalpy (PeleLM_K.H:84-86): reactor_type must be 2");
   const int ns = r->tables->ns;
   if (rhoY.ncomp < ns || rhoYdot.ncomp < ns) return fail(PLM_ERR_ARG, "rhoY/rhoYdot need NUM_SPECIES components");
   for (int d = 0; d < 3; ++d) {

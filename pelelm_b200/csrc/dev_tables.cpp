@@ -54,6 +54,13 @@ int build_dev_mech(const plm_mech_tables* t, DevMechOwner* out)
     return v;
   };
   std::vector<double> cp = plane(t->cp, 5), h = plane(t->h, 6), g = plane(t->g, 7), dcp = plane(t->dcp, 4);
+  // cv_R / speciesInternalEnergy: the same polynomials with the constant term a0 - 1 (tables: a0m1)
+  std::vector<double> cpe = cp, he = h;
+  for (int k = 0; k < ns; ++k)
+    for (int r = 0; r < 2; ++r) {
+      cpe[(size_t(r) * 5 + 0) * nsp + k] = t->a0m1[k * 2 + r];
+      he[(size_t(r) * 6 + 0) * nsp + k] = t->a0m1[k * 2 + r];
+    }
 
   std::vector<double> A(nrp, 0.0), b(nrp, 0.0), EaR(nrp, 0.0), A0(nrp, 0.0), b0(nrp, 0.0), Ea0R(nrp, 0.0);
   std::vector<double> ta(nrp, 0.0), tiT3(nrp, 0.0), tiT1(nrp, 0.0), tT3(nrp, 1.0), tT1(nrp, 1.0), tT2(nrp, 0.0);
@@ -248,7 +255,7 @@ int build_dev_mech(const plm_mech_tables* t, DevMechOwner* out)
                o_em = bl.add(em1), o_so = bl.add(soff), o_sr = bl.add(sreac), o_sn = bl.add(snu),
                o_no = bl.add(noff), o_ni = bl.add(nidx), o_nn = bl.add(nnu), o_rp0 = bl.add(rp0), o_rp1 = bl.add(rp1),
                o_fo0 = bl.add(fo0), o_fo1 = bl.add(fo1), o_fo2 = bl.add(fo2), o_fo3 = bl.add(fo3), o_fo4 = bl.add(fo4),
-               o_eff = bl.add(eff), o_gat = bl.add(gat), o_seg = bl.add(seg);
+               o_eff = bl.add(eff), o_gat = bl.add(gat), o_seg = bl.add(seg), o_cpe = bl.add(cpe), o_he = bl.add(he);
   (void)o_dcp; (void)o_so; (void)o_sr; (void)o_sn;
   static_assert(sizeof(DevMech) <= 512, "DevMech header");
   void* dev = nullptr;
@@ -258,6 +265,8 @@ int build_dev_mech(const plm_mech_tables* t, DevMechOwner* out)
   auto I = [&](size_t o) { return reinterpret_cast<const int*>(base + o); };
   d.mw = D(o_mw); d.imw = D(o_imw); d.tmid = D(o_tmid);
   d.cp = D(o_cp); d.h = D(o_h); d.g = D(o_g);
+  d.eint = 0;
+  out->cp_h = D(o_cp); out->h_h = D(o_h); out->cp_e = D(o_cpe); out->h_e = D(o_he);
   auto D2 = [&](size_t o) { return reinterpret_cast<const double2*>(base + o); };
   d.rp0 = D2(o_rp0); d.rp1 = D2(o_rp1); d.fo0 = D2(o_fo0); d.fo1 = D2(o_fo1); d.fo2 = D2(o_fo2); d.fo3 = D2(o_fo3);
   d.fo4 = D(o_fo4); d.eff = D2(o_eff);
@@ -281,6 +290,16 @@ int build_dev_mech(const plm_mech_tables* t, DevMechOwner* out)
   out->blob = dev;
   out->blob_bytes = bl.bytes.size();
   return 0;
+}
+
+int select_reactor_type(DevMechOwner* o, int reactor_type)
+{
+  if (!o || !o->blob) return -1;
+  const bool e = reactor_type == 1;
+  o->h.eint = e ? 1 : 0;
+  o->h.cp = e ? o->cp_e : o->cp_h;
+  o->h.h = e ? o->h_e : o->h_h;
+  return cudaMemcpy(o->blob, &o->h, sizeof(DevMech), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -2;
 }
 
 void free_dev_mech(DevMechOwner* o)

@@ -31,7 +31,7 @@ struct DevMech {
   int n3b_end;  // reactions [nfall, n3b_end) are three-body; n3b_end <= 32
   int emax;     // longest third-body efficiency list
   int glen;     // gather segment length (entries per lane-slot)
-  int pad_;
+  int eint;     // 1: internal-energy reactor (ode.reactor_type = 1): cp/h below are the cv/R and e/RT planes
   // species
   const double *mw, *imw, *tmid;
   const double *cp;   // [2][5][nsp_pad]
@@ -59,6 +59,8 @@ struct DevMech {
 
 // Host-side owner: builds the arrays from the flat tables and uploads them. Returns nonzero on failure.
 struct DevMechOwner {
+  const double *cp_h = nullptr, *h_h = nullptr;  // cp/R, h/RT planes (enthalpy reactor)
+  const double *cp_e = nullptr, *h_e = nullptr;  // cv/R, e/RT planes (internal-energy reactor): constant term a0 - 1
   DevMech h{};        // host copy of the struct holding DEVICE pointers
   const DevMech* d = nullptr;  // the same struct in device memory (first bytes of the blob)
   void* blob = nullptr;
@@ -66,5 +68,8 @@ struct DevMechOwner {
 };
 int build_dev_mech(const plm_mech_tables* t, DevMechOwner* out);   // 0 ok
 void free_dev_mech(DevMechOwner* o);
+// ode.reactor_type: 1 = internal energy (REY2T / Ei / Cv; consP = 0 in the Jacobian), 2 = enthalpy. Re-points the thermo
+// planes of the descriptor and refreshes its device copy. Returns nonzero on failure.
+int select_reactor_type(DevMechOwner* o, int reactor_type);
 
 }  // namespace plm

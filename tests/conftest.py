@@ -46,6 +46,11 @@ def golden_plm(mech):
     return np.load(os.path.join(GOLDEN, mech + "_plm.npz"))
 
 
+def golden_e(mech):
+    """the internal-energy reactor (ode.reactor_type = 1): tests/golden/<mech>_e.npz"""
+    return np.load(os.path.join(GOLDEN, mech + "_e.npz"))
+
+
 def scaled_err(a, ref, rtol, atol):
     """max |a-ref| / (rtol*|ref| + atol): <= 1 means within the stated tolerance."""
     return float(np.max(np.abs(a - ref) / (rtol * np.abs(ref) + atol))) if ref.size else 0.0

@@ -116,6 +116,43 @@ def extra(mech: str):
     print(mech, "PeleLM-side golden written:", len(out), "arrays")
 
 
+def etype(mech: str):
+    """tests/golden/<mech>_e.npz: the internal-energy reactor (ode.reactor_type = 1, the ReactEval default:
+    REY2T / RTY2Ei / RTY2Cv in fKernelSpec, ReactorUtils.H:300-316, consP = 0 in cJac, ReactorCvodeJacobian.cpp:109-118)."""
+    from oracle.pyoracle import Ref
+    from pelelm_b200 import synth
+    R = Ref(mech)
+    out = {}
+    P_ATM = 1013250.0
+    nc = NCELLS[mech]
+    for name, integ, ikw in (("cv_e", "ReactorCvode", dict(rtol=1e-8, atol=1e-10, max_order=2)),
+                             ("rk_e", "ReactorRK64", dict(atol=1e-10))):
+        if name == "rk_e" and mech == "dodecane_lu":
+            continue
+        b = synth.synthetic_batch(mech, nc, seed=synth.DEFAULT_SEED + 201, dt=DT, forcing=True, mask_every=7,
+                                  t_range=(900.0, 1150.0) if name == "rk_e" else (900.0, 2600.0))
+        b["rE"] = b["rE"] - P_ATM   # rho*e = rho*h - p
+        R.init(integrator=integ, reactor_type=1, **ikw)
+        R.set_typ_vals(np.full(R.n, -1.0))
+        rY, T, rE, FC = R.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT)
+        for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask"):
+            out[name + "/in_" + k] = b[k]
+        out[name + "/rY"], out[name + "/T"], out[name + "/rE"], out[name + "/FC"] = rY, T, rE, FC
+    b = synth.synthetic_batch(mech, 32, seed=78, forcing=True, dt=DT)
+    y = np.ascontiguousarray(np.concatenate([b["rY"].T, b["T"][:, None]], 1))
+    rYsrc = np.ascontiguousarray(b["rYsrc"].T)
+    rE = b["rE"] - P_ATM
+    out["rhs/y"], out["rhs/rhoe"], out["rhs/rhoesrc"], out["rhs/rYsrc"] = y, rE, b["rEsrc"], rYsrc
+    out["rhs/t"] = np.array(3e-6)
+    out["rhs/ydot"] = R.rhs(y, rE, b["rEsrc"], rYsrc, 3e-6, reactor_type=1)
+    y2 = y.copy()
+    y2[:, -1] = b["T_true"]
+    out["jac/y"] = y2
+    out["jac/J"] = R.jac(y2, reactor_type=1)
+    np.savez_compressed(os.path.join(HERE, mech + "_e.npz"), **out)
+    print(mech, "e-reactor golden written:", len(out), "arrays")
+
+
 def knap():
     """KnapSackProcessorMap buckets from the reference's own knapsack() (any libref works)."""
     import ctypes as C
@@ -160,12 +197,19 @@ def vismf():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "vismf":
         vismf()
+    elif len(sys.argv) > 2 and sys.argv[1] == "etype":
+        etype(sys.argv[2])
+    elif len(sys.argv) > 1 and sys.argv[1] == "etype":
+        for m in NCELLS:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "etype", m])
     elif len(sys.argv) > 2 and sys.argv[1] == "extra":
         extra(sys.argv[2])
     elif len(sys.argv) > 1 and sys.argv[1] == "extra":  # only the PeleLM-side fixtures (the others stay as committed)
         for m in NCELLS:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "extra", m])
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "vismf"])
+        for m in NCELLS:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "etype", m])
     elif len(sys.argv) > 1:
         knap() if sys.argv[1] == "knapsack" else one(sys.argv[1])
     else:
@@ -174,4 +218,6 @@ if __name__ == "__main__":
         for m in NCELLS:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "extra", m])
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "vismf"])
+        for m in NCELLS:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "etype", m])
 

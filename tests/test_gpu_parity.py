@@ -7,7 +7,7 @@ identical mask/skip behaviour; rhoH bit-exact; FC identical where the port's is.
 import numpy as np
 import pytest
 
-from conftest import MECHS, golden, golden_plm, check_state
+from conftest import MECHS, golden, golden_plm, golden_e, check_state
 from golden.make_golden import CASES, DT
 
 pytestmark = pytest.mark.gpu
@@ -353,3 +353,37 @@ def test_subcycled_calls_with_advancing_time(capi, port_lib, mech, integ):
         check_state((g[0], g[2], g[3], g[5]), (rY, T, rE, FC), 1e-10, tag="%s step %d" % (mech, k), rtol=2e-6, fc_rel=0.05)
     R.close()
     assert np.array_equal(g[3], p[2])  # rhoH: in + dt*src three times, bit-exact
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_internal_energy_reactor_vs_reference(capi, mech):
+    """init(reactor_type = 1, ...) (ReactorBase.H:20; the ReactEval default): RHS, Jacobian (consP = 0) and both
+    integrators against the reference run with ode.reactor_type = 1."""
+    g = golden_e(mech)
+    R = capi.Reactor(mech, "ReactorCvode").init(reactor_type=1)
+    f = R.eval_rhs(g["rhs/y"], g["rhs/rhoe"], g["rhs/rhoesrc"], g["rhs/rYsrc"], float(g["rhs/t"]))
+    assert (np.abs(f - g["rhs/ydot"]) / np.abs(g["rhs/ydot"]).max(1, keepdims=True)).max() < 1e-9
+    J = R.eval_jac(g["jac/y"])
+    assert (np.abs(J - g["jac/J"]) / np.abs(g["jac/J"]).max(1, keepdims=True)).max() < 1e-9
+    R.close()
+    small = mech != "dodecane_lu"
+    for case, integ, ikw in (("cv_e", "ReactorCvode", dict(rtol=1e-8, atol=1e-10, max_order=2)),
+                             ("rk_e", "ReactorRK64", dict(rtol=1e-10, atol=1e-10))):
+        if case + "/rY" not in g:
+            continue
+        b = {k: g[case + "/in_" + k] for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask")}
+        nc = b["T"].size
+        R = capi.Reactor(mech, integ).init(reactor_type=1, **ikw)
+        a = [b["rY"].copy(), b["rYsrc"].copy(), b["T"].copy(), b["rE"].copy(), b["rEsrc"].copy(), np.zeros(nc)]
+        R.react([0, 0, 0], [nc - 1, 0, 0], a[0], a[1], a[2], a[3], a[4], a[5], b["mask"].copy(), DT)
+        assert not R.cell_status(nc).any()
+        R.close()
+        ref = (g[case + "/rY"], g[case + "/T"], g[case + "/rE"], g[case + "/FC"])
+        check_state((a[0], a[2], a[3], a[5]), ref, 1e-10, tag="%s/%s" % (mech, case), rtol=1e-6,
+                    fc_equal_min=0.9 if small else None, fc_rel=0.05 if small else 0.2)
+    # the enthalpy-only entry point refuses an internal-energy reactor
+    R = capi.Reactor(mech, "ReactorCvode").init(reactor_type=1)
+    with pytest.raises(Exception):
+        z = np.zeros((R.ns, 1))
+        R.reaction_rate_rhoY([0, 0, 0], [0, 0, 0], z + 1.0, np.ones(1), np.full(1, 1000.0), None, z.copy())
+    R.close()

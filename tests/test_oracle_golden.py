@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import MECHS, golden, golden_plm, check_state, scaled_err
+from conftest import MECHS, golden, golden_plm, golden_e, check_state, scaled_err
 from golden.make_golden import CASES, DT
 
 
@@ -117,3 +117,26 @@ def test_port_advance_chemistry_vs_reference(port_lib, mech):
     ref = g["advchem/IR"]
     e = np.abs(IR - ref) / (1e-6 * np.abs(ref) + 1e-6 * np.abs(ref).max(0, keepdims=True) + 1e-7 / DT)
     assert e.max() <= 1.0, e.max()
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_port_internal_energy_reactor_vs_reference(port_lib, mech):
+    """ode.reactor_type = 1 (the ReactEval default): fKernelSpec with REY2T / Ei / Cv, cJac with consP = 0 -- including
+    the stale dqdc[] entries of the generated aJacobian, see oracle/port/chem.c -- and both integrators."""
+    g = golden_e(mech)
+    P = port_lib.Port(mech)
+    f = P.rhs(g["rhs/y"], g["rhs/rhoe"], g["rhs/rhoesrc"], g["rhs/rYsrc"], float(g["rhs/t"]), reactor_type=1)
+    assert (np.abs(f - g["rhs/ydot"]) / np.abs(g["rhs/ydot"]).max(1, keepdims=True)).max() < 1e-9
+    J = P.jac(g["jac/y"], reactor_type=1)
+    assert (np.abs(J - g["jac/J"]) / np.abs(g["jac/J"]).max(1, keepdims=True)).max() < 1e-9
+    small = mech != "dodecane_lu"
+    for case, integ, ikw in (("cv_e", "ReactorCvode", dict(rtol=1e-8, atol=1e-10, max_order=2)),
+                             ("rk_e", "ReactorRK64", dict(rtol=1e-10, atol=1e-10))):
+        if case + "/rY" not in g:
+            continue
+        P.init(integrator=integ, reactor_type=1, **ikw)
+        b = {k: g[case + "/in_" + k] for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask")}
+        got = P.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT, nthreads=4)
+        ref = (g[case + "/rY"], g[case + "/T"], g[case + "/rE"], g[case + "/FC"])
+        check_state(got, ref, 1e-10, tag="%s/%s" % (mech, case), rtol=1e-6, fc_equal_min=0.9 if small else None,
+                    fc_rel=0.05 if small else 0.2)
