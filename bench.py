@@ -325,14 +325,12 @@ def run_gpu_arm(a):
     for w in range(max(a.warmup, 1)):
         gst, full, new_owner, eff = step()
         if w == 0 and N > 1 and not np.array_equal(new_owner, owner):
-            for key in ("hS", "hF", "hmask"):
-                payload = {b: boxes[b][key].to(dev) for b in boxes if owner[b] == rank}
-                moved = pd.redistribute(payload, owner, new_owner)
-                for b, t in moved.items():
-                    boxes.setdefault(b, {"id": b})[key] = t.cpu().pin_memory()
-            for b in list(boxes):
-                if new_owner[b] != rank:
-                    del boxes[b]
+            moved = pd.move_boxes(boxes, ("hS", "hF", "hmask"), owner, new_owner, device=dev)
+            for b, bx in moved.items():
+                if owner[b] != rank:  # received: back to pinned host memory, where the e2e leg reads it
+                    for key in ("hS", "hF", "hmask"):
+                        bx[key] = bx[key].cpu().pin_memory()
+            boxes = moved
             owner = new_owner.copy()
             for bx in boxes.values():
                 to_device(bx)

@@ -148,3 +148,21 @@ def redistribute(payload: dict, old_owner, new_owner, group=None):
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return out
+
+
+def move_boxes(boxes: dict, keys, old_owner, new_owner, device=None, group=None):
+    """Re-home whole boxes after a new distribution map (advance_chemistry's ParallelCopy into the chemistry MultiFabs,
+    PeleLM.cpp:5692-5697): `boxes` = {box id: {key: tensor}} of the boxes this rank owns under old_owner; every tensor
+    named in `keys` travels; returns the dict of the boxes owned under new_owner (tensors of received boxes live on
+    `device`, kept boxes are the original objects)."""
+    old_owner, new_owner = np.asarray(old_owner), np.asarray(new_owner)
+    rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+    mine = [b for b in boxes if old_owner[b] == rank]
+    out = {b: dict(boxes[b]) for b in mine if new_owner[b] == rank}
+    for key in keys:
+        payload = {b: (boxes[b][key].to(device) if device is not None else boxes[b][key]) for b in mine}
+        moved = redistribute(payload, old_owner, new_owner, group=group)
+        for b, t in moved.items():
+            if old_owner[b] != rank:
+                out.setdefault(b, {"id": b})[key] = t
+    return out

@@ -42,6 +42,14 @@ def _worker(rank, ws, port, q):
     assert sorted(got) == sorted(int(b) for b in np.nonzero(new_owner == rank)[0])
     for b, t in got.items():
         assert torch.all(t == float(b))
+    # whole boxes with several arrays each (what bench.py / a PeleLM driver moves after the first knapsack pass)
+    boxes = {int(b): {"id": int(b), "S": torch.full((2, 5), float(b)), "F": torch.full((3,), -float(b)),
+                      "m": torch.full((5,), int(b), dtype=torch.int32)} for b in mine}
+    moved = pd.move_boxes(boxes, ("S", "F", "m"), owner, new_owner)
+    assert sorted(moved) == sorted(int(b) for b in np.nonzero(new_owner == rank)[0])
+    for b, bx in moved.items():
+        assert torch.all(bx["S"] == float(b)) and torch.all(bx["F"] == -float(b)) and torch.all(bx["m"] == int(b))
+        assert bx["m"].dtype == torch.int32 and tuple(bx["S"].shape) == (2, 5)
     st = pd.reduce_stats({"ncells": 10 + rank, "nfe": 100 * (rank + 1), "max_fc": 5 + rank, "min_fc": 3 - rank,
                           "kernel_ms": 1.0 + rank})
     q.put((rank, new_owner.tolist(), eff, st))
