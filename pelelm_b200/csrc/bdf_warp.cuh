@@ -107,17 +107,26 @@ __device__ __noinline__ int gjinv_warp()
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(kFull, v, o);
-      const int oi = __shfl_xor_sync(kFull, idx, o);
-      if (ov > v || (ov == v && oi < idx)) {
-        v = ov;
-        idx = oi;
-      }
+    {
+      // arg-max over the warp with three hardware reductions (redux.sync) instead of a 5-level butterfly of
+      // (value, index) pairs: non-negative doubles order like their bit patterns, so the maximum is the maximum of the
+      // high words, then of the low words among those, and the first row wins ties (denseGETRF's rule). A NaN entry
+      // (never larger in the reference's comparison) gets the smallest key.
+      const bool ok = v >= 0.0;  // false for "no candidate row in this lane" (v = -1) and for NaN
+      const unsigned hi = ok ? unsigned(__double2hiint(v)) + 1u : 0u;  // +1: a valid zero pivot candidate still beats "none"
+      const unsigned mhi = __reduce_max_sync(kFull, hi);
+      const bool c1 = ok && hi == mhi;
+      const unsigned lo = c1 ? unsigned(__double2loint(v)) : 0u;
+      const unsigned mlo = __reduce_max_sync(kFull, lo);
+      const bool win = c1 && lo == mlo;
+      const unsigned first = __reduce_min_sync(kFull, win ? unsigned(idx) : 0x7fffffffu);
+      const int src = int(first & 31u);  // the winner row's lane (rows are lane + 32 * slot)
+      v = __shfl_sync(kFull, v, src);
+      idx = (mhi == 0u) ? 0x7fffffff : int(first);
+      if (mhi == 0u) v = -1.0;
     }
     const int l = idx;
-    if (v == 0.0) return k + 1;
+    if (!(v > 0.0)) return k + 1;  // zero pivot column (or nothing but NaN in it): singular
     const double pivinv = 1.0 / A[l * ld + k];
     __syncwarp();
     // swap rows l and k and scale the pivot row: lane = column
