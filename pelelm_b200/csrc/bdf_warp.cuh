@@ -107,7 +107,17 @@ __device__ __noinline__ int gjinv_warp()
         }
       }
     }
-    {
+    if (!L::BIG) {  // small systems: the butterfly measured 4 % faster on drm19 than the reductions below
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(kFull, v, o);
+        const int oi = __shfl_xor_sync(kFull, idx, o);
+        if (ov > v || (ov == v && oi < idx)) {
+          v = ov;
+          idx = oi;
+        }
+      }
+    } else {
       // arg-max over the warp with three hardware reductions (redux.sync) instead of a 5-level butterfly of
       // (value, index) pairs: non-negative doubles order like their bit patterns, so the maximum is the maximum of the
       // high words, then of the low words among those, and the first row wins ties (denseGETRF's rule). A NaN entry
