@@ -96,20 +96,12 @@ def _mixture_state(m: Mech, X: np.ndarray, T: np.ndarray, p: float = P_ATM):
     return Y, rho, h
 
 
-def synthetic_batch(mech_name: str, ncells: int, seed: int = DEFAULT_SEED, cell0: int = 0, forcing: bool = False,
-                    dt: float = 1e-5, mask_every: int = 0, t_range=(900.0, 2600.0)):
-    """Component-major (FAB layout) arrays of one batch: dict with rY [ns][nc], rYsrc [ns][nc], T, rE, rEsrc, mask.
-
-    T holds the initial GUESS handed to react (true T + up to +-30 K), as PeleLM hands over a lagged temperature.
-    forcing=True adds src_k ~ U[-1,1] 1e-2 rhoY_k/dt with zero net mass and rhoh_src ~ U[-1,1] 1e-2 |rho h|/dt.
-    mask_every=k marks every k-th global cell -1 (ReactorCvode skips it; ReactorRK64 ignores the mask).
-    """
-    m = mech(mech_name)
+def flame_state(m: Mech, mech_name: str, T: np.ndarray, phi: np.ndarray, c: np.ndarray, urad: np.ndarray,
+                p: float = P_ATM):
+    """Mass fractions, density and enthalpy (CGS) of fuel/air at equivalence ratio phi, blended with its complete-combustion
+    products (+ OH, H, O, HO2 at levels scaled by urad[0..3] in [0,1]) by the burnt fraction c, at temperature T, pressure p."""
+    ncells = T.shape[0]
     ns = m.ns
-    u = uniforms(seed, cell0, ncells, 8 + 2 * ns)
-    T = t_range[0] + (t_range[1] - t_range[0]) * u[0]
-    phi = 0.5 * np.exp(np.log(4.0) * u[1])
-    c = u[2]
     fuel = FUEL[mech_name]
     x, y = FUEL_CH[fuel]
     a = x + y / 4.0  # O2 per fuel at stoichiometry
@@ -134,13 +126,31 @@ def synthetic_batch(mech_name: str, ncells: int, seed: int = DEFAULT_SEED, cell0
     Xb[:, m.idx("O2")] += np.maximum(left, 0.0) / 2.0
     Xb /= Xb.sum(1, keepdims=True)
     for sp, lvl, s in (("OH", 3e-3, 3), ("H", 1e-3, 4), ("O", 1e-3, 5), ("HO2", 1e-5, 6)):
-        Xb[:, m.idx(sp)] += lvl * (0.1 + 0.9 * u[s])
+        Xb[:, m.idx(sp)] += lvl * (0.1 + 0.9 * urad[s - 3])
     Yf, _, _ = _mixture_state(m, Xf, T)
     Yb, _, _ = _mixture_state(m, Xb, T)
     Y = (1.0 - c)[:, None] * Yf + c[:, None] * Yb
     wbar_inv = (Y / m.mw[None, :]).sum(1)
-    rho = P_ATM / (RU * T * wbar_inv)
+    rho = p / (RU * T * wbar_inv)
     h = (Y * m.h_mass(T)).sum(1)
+    return Y, rho, h
+
+
+def synthetic_batch(mech_name: str, ncells: int, seed: int = DEFAULT_SEED, cell0: int = 0, forcing: bool = False,
+                    dt: float = 1e-5, mask_every: int = 0, t_range=(900.0, 2600.0)):
+    """Component-major (FAB layout) arrays of one batch: dict with rY [ns][nc], rYsrc [ns][nc], T, rE, rEsrc, mask.
+
+    T holds the initial GUESS handed to react (true T + up to +-30 K), as PeleLM hands over a lagged temperature.
+    forcing=True adds src_k ~ U[-1,1] 1e-2 rhoY_k/dt with zero net mass and rhoh_src ~ U[-1,1] 1e-2 |rho h|/dt.
+    mask_every=k marks every k-th global cell -1 (ReactorCvode skips it; ReactorRK64 ignores the mask).
+    """
+    m = mech(mech_name)
+    ns = m.ns
+    u = uniforms(seed, cell0, ncells, 8 + 2 * ns)
+    T = t_range[0] + (t_range[1] - t_range[0]) * u[0]
+    phi = 0.5 * np.exp(np.log(4.0) * u[1])
+    c = u[2]
+    Y, rho, h = flame_state(m, mech_name, T, phi, c, u[3:7])
     rY = np.ascontiguousarray((Y * rho[:, None]).T)
     rE = rho * h
     Tguess = T + 60.0 * (u[7] - 0.5)
