@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="batch", choices=["batch", "tripleflame"],
+                    help="batch: BASELINE.json configs[1-3] (default); tripleflame: configs[4], per-level chemistry of a synthetic "
+                         "3-level AMR hierarchy with cost-weighted box distribution (pelelm_b200/amr.py)")
+    ap.add_argument("--amr-n0", default="32,64,32", help="level-0 cells of the tripleflame hierarchy (SURVEY cfg5: 64,128,64)")
     return ap.parse_args()
 
 
@@ -437,10 +441,116 @@ def run_gpu_arm(a):
         dist.destroy_process_group()
 
 
+def run_amr_arm(a):
+    """BASELINE.json configs[4]: one step = one PeleLM::advance_chemistry of every level of the synthetic TripleFlame
+    hierarchy (dt_L = dt / 2^L), boxes dealt over the GPUs by the knapsack on the previous pass's FC (state map = round
+    robin), box payloads moved to the chemistry owner and back, covered I_R averaged down.  Strong scaling: the hierarchy
+    is the same for every N."""
+    import torch
+    import torch.distributed as dist
+    from pelelm_b200 import amr, capi, roofline
+    from pelelm_b200 import dist as pd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    N = world
+    capi.load()
+    n0 = tuple(int(x) for x in a.amr_n0.split(","))
+    R = capi.Reactor(a.mech, a.integrator).init(rtol=a.rtol, atol=a.atol, max_order=a.max_order)
+    peak_tf = capi.measure_fp64_peak()
+    levels = amr.build_tripleflame(a.mech, N, rank, n0=n0, nlev=3, box=32, device=dev, dt=DT)
+    for L in levels:
+        for bx in L.data.values():
+            bx["S0"] = bx["S"].clone()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
+    adv, wait_k = amr.gpu_advance(R, streams)
+    tot = {}
+
+    def wait():
+        st = wait_k()
+        for k, v in st.items():
+            tot[k] = max(tot.get(k, 0), v) if k in ("max_fc", "min_fc", "kernel_ms") else tot.get(k, 0) + v
+
+    def step():
+        infos = []
+        for L in levels:
+            for bx in L.data.values():
+                bx["S"].copy_(bx["S0"], non_blocking=True)   # every step from the same pristine state; FC is kept: the costs
+            fine = levels[L.lev + 1] if L.lev + 1 < len(levels) else None
+            infos.append(amr.advance_chemistry_level(L, DT / 2 ** L.lev, adv, fine=fine, cost_fn=capi.box_costs, wait=wait,
+                                                     device=dev))
+        return infos
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 1)):
+        infos = step()
+    barrier()
+    tot.clear()
+    adv.launches[0] = 0
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        infos = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    gst = pd.reduce_stats(tot)
+    launches = adv.launches[0] + a.steps * sum(1 for L in levels if L.data)   # advances + one box-cost reduction per level
+    if N > 1:
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        ms, launches = float(t[0].item()), int(t[1].item())
+    if rank == 0:
+        ncell = [L.ncells() for L in levels]
+        cells_total = sum(ncell)
+        value = cells_total * a.steps / (ms * 1e-3)
+        flops = roofline.algorithmic_flops(a.mech, a.integrator, gst)
+        achieved = flops / (ms * 1e-3) * 1e-12 / N
+        per_cell = {k: gst[k] / max(gst["ncells"], 1) for k in ("nst", "nfe", "nje", "nsetups", "nni", "netf", "ncfn")}
+        line = {
+            "metric": "chemistry cells*dt/s", "value": value, "unit": "cells*dt/s", "n_gpus": N, "steps": a.steps,
+            "warmup": max(a.warmup, 1), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 3-level TripleFlame AMR, %s %s denseAJ_direct rtol=%g atol=%g max_order=%d, level-0 %s cells, "
+                                   "boxes of 32^3 per level %s, cells per level %s, dt_L = %g/2^L"
+                                   % (a.mech, a.integrator, a.rtol, a.atol, a.max_order, "x".join(map(str, n0)),
+                                      [len(L.boxes) for L in levels], ncell, DT),
+                       "l2": "inputs larger than L2 (%.2f GB state)" % (cells_total * roofline.state_bytes_per_cell(a.mech) / 1e9),
+                       "parallelism": "boxes of every level over %d GPU(s), knapsack on the previous pass's FC" % N,
+                       "knapsack_efficiency": [i["efficiency"] for i in infos], "boxes_moved": [i["moved"] for i in infos],
+                       "per_cell": per_cell, "nfailed": gst["nfailed"]},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "DFMA probe measured live on this device (MEASURED_PEAKS.json has no FP64 entry)",
+                         "flops_per_cell": flops / max(gst["ncells"], 1)},
+            "clocks": clk, "e2e": None, "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+    R.close()
+    if N > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.workload == "tripleflame":
+        run_amr_arm(a)
     else:
         run_gpu_arm(a)
 

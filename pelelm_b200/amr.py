@@ -253,3 +253,31 @@ def advance_hierarchy(levels, dt, advance_box, **kw):
         fine = levels[L.lev + 1] if L.lev + 1 < len(levels) else None
         out.append(advance_chemistry_level(L, dt / 2 ** L.lev, advance_box, fine=fine, **kw))
     return out
+
+
+def gpu_advance(reactor, streams=None):
+    """(advance_box, wait) for advance_chemistry_level on the GPU: one fused `plm_advance_chemistry_box` launch per box
+    (device arrays, the box as its own FAB), launches spread round robin over `streams`; wait() drains them and returns
+    the integrator statistics accumulated since the previous wait()."""
+    ns = reactor.ns
+    launches = [0]
+
+    def advance_box(bx, shape, dt, slot):
+        S, F = bx["S"], bx["F"]
+        st = streams[slot % len(streams)] if streams else None
+        lo, hi = [0, 0, 0], [shape[0] - 1, shape[1] - 1, shape[2] - 1]
+        if st is not None:
+            st.wait_stream(torch.cuda.current_stream())
+        reactor.advance_chemistry(lo, hi, S[:ns], S[ns], S[ns + 1], F[:ns], F[ns], bx["I_R"], bx["FC"], bx["mask"], dt,
+                                  stream=st.cuda_stream if st is not None else None, sync=False)
+        launches[0] += 1
+
+    def wait():
+        out = reactor.stats()   # waits for every outstanding launch of this reactor
+        if streams:
+            for st in streams:
+                torch.cuda.current_stream().wait_stream(st)
+        return out
+
+    advance_box.launches = launches
+    return advance_box, wait

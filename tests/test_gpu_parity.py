@@ -387,3 +387,72 @@ def test_internal_energy_reactor_vs_reference(capi, mech):
         z = np.zeros((R.ns, 1))
         R.reaction_rate_rhoY([0, 0, 0], [0, 0, 0], z + 1.0, np.ones(1), np.full(1, 1000.0), None, z.copy())
     R.close()
+
+
+def test_amr_levels_vs_port(capi, port_lib):
+    """BASELINE.json configs[4]: per-level chemistry of the synthetic 3-level TripleFlame hierarchy through
+    pelelm_b200/amr.py (costs by the library's box-cost kernel, knapsack, one fused advance_chemistry launch per box on
+    several streams, average-down), against the same driver run around the port's react on the CPU for levels 0 and 1
+    (they do not depend on level 2's results within three steps except through the average-down, checked separately)."""
+    import torch
+    from pelelm_b200 import amr
+    import test_amr_cpu as tc
+    mech, n0, box, nsteps = tc.MECH, (8, 16, 8), 8, 3
+    R = capi.Reactor(mech, "ReactorCvode").init(rtol=1e-8, atol=1e-10, max_order=2)
+    ns = R.ns
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    adv, wait = amr.gpu_advance(R, streams)
+    dev = amr.build_tripleflame(mech, 1, 0, n0=n0, nlev=3, box=box, device="cuda", forcing=True, dt=DT)
+    fc_sums = {}
+    fine_first = None
+    for step in range(nsteps):
+        for L in dev:
+            fine = dev[L.lev + 1] if L.lev + 1 < len(dev) else None
+            info = amr.advance_chemistry_level(L, DT / 2 ** L.lev, adv, fine=fine, cost_fn=capi.box_costs, wait=wait)
+            # the weights of getFuncCountDM: FC = 1 per cell before the first pass, then what the previous pass wrote
+            want = [box ** 3] * len(L.boxes) if step == 0 else fc_sums[L.lev]
+            assert info["costs"].tolist() == want
+            assert info["moved"] == 0 and (info["chem_owner"] == 0).all()
+            fc_sums[L.lev] = [int(L.data[b]["FC"].sum().item()) for b in sorted(L.data)]
+        if step == 0:
+            fine_first = {b: bx["I_R"].clone() for b, bx in dev[2].data.items()}
+    torch.cuda.synchronize()
+    assert adv.launches[0] == nsteps * sum(len(L.boxes) for L in dev)
+    assert not R.cell_status(box ** 3).any()
+    R.close()
+    # level 1's covered cells after its 3rd advance = mean of level 2's OLD I_R at that moment = level 2's 1st result
+    L1, L2 = dev[1], dev[2]
+    ncov = 0
+    for f, (lo, hi) in enumerate(L2.boxes):
+        c = [i for i, (clo, chi) in enumerate(L1.boxes) if all(clo[d] <= lo[d] // 2 and hi[d] // 2 <= chi[d] for d in range(3))]
+        assert len(c) == 1
+        c = c[0]
+        v = fine_first[f].reshape(ns, box // 2, 2, box // 2, 2, box // 2, 2).mean(dim=(2, 4, 6))
+        o = [lo[d] // 2 - L1.boxes[c][0][d] for d in range(3)]
+        got = L1.data[c]["I_R"].reshape(ns, box, box, box)[:, o[2]:o[2] + box // 2, o[1]:o[1] + box // 2, o[0]:o[0] + box // 2]
+        assert torch.equal(got, v)
+        ncov += v[0].numel()
+    assert 0 < ncov < L1.ncells()
+    # levels 0 and 1 against the port: uncovered cells only (covered I_R comes from the finer level, checked above)
+    cpu = amr.build_tripleflame(mech, 1, 0, n0=n0, nlev=3, box=box, forcing=True, dt=DT)
+    padv = tc._port_advance()
+    for _ in range(nsteps):
+        for L in cpu[:2]:
+            amr.advance_chemistry_level(L, DT / 2 ** L.lev, padv, fine=None, use_knapsack=False)
+    for l in range(2):
+        fineb = dev[l + 1].boxes
+        for b in cpu[l].data:
+            g = {k: dev[l].data[b][k].cpu().numpy() for k in ("S", "I_R", "FC")}
+            r = {k: cpu[l].data[b][k].numpy() for k in ("S", "I_R", "FC")}
+            ref = (r["S"][:ns], r["S"][ns + 1], r["S"][ns], r["FC"])
+            got = (g["S"][:ns], g["S"][ns + 1], g["S"][ns], g["FC"])
+            check_state(got, ref, 1e-7, tag="amr L%d box %d" % (l, b), rtol=1e-6, fc_rel=0.05)
+            cov = np.zeros((box, box, box), dtype=bool)
+            blo = cpu[l].boxes[b][0]
+            for lo, hi in fineb:
+                o = [lo[d] // 2 - blo[d] for d in range(3)]
+                if all(0 <= o[d] < box for d in range(3)):
+                    cov[o[2]:o[2] + box // 2, o[1]:o[1] + box // 2, o[0]:o[0] + box // 2] = True
+            unc = ~cov.ravel()
+            sc = 1e-6 * np.abs(r["I_R"]) + 1e-6 * np.abs(r["I_R"]).max(1, keepdims=True) + 1e-7 / DT
+            assert (np.abs(g["I_R"] - r["I_R"]) <= sc)[:, unc].all(), (l, b)
