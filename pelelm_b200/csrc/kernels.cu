@@ -247,7 +247,6 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
             sv = __dmul_rn(sv, 1.0e-3);
           }
           wb[L::SRC + k] = sv;
-          wb[L::RY0 + k] = ry0[s];
         }
         if (lane == 0) {
           wb[L::SM + 24] = rhoe_init;
@@ -264,7 +263,6 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
           const int k = lane + 32 * s;
           y[s] = clean ? fmin(fmax(0.0, ry0[s]), rho_old) : ry0[s];
           if (k >= ns) y[s] = 0.0;
-          wb[L::CLIP + k] = y[s];
         }
       }
       double T0 = Tin, rho_oldclipped = 0.0;
@@ -308,7 +306,12 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
       for (int s = 0; s < NSLOT; ++s) {
         const int k = lane + 32 * s;
         outv[s] = y[s];
-        if (clean) outv[s] = wb[L::RY0 + k] + (y[s] - wb[L::CLIP + k]) * wb[L::SM + 56] / wb[L::SM + 57];
+        if (clean) {  // ReactorUtils.H:160-166: the loaded and the clipped state, recomputed from the value still in the FAB
+          double r0 = (k < ns) ? a.rY.p[ad.oY + int64_t(k) * ad.sY] : 0.0;
+          if (mks) r0 = __dmul_rn(r0, 1.0e-3);
+          const double cl = (k < ns) ? fmin(fmax(0.0, r0), wb[L::SM + 56]) : 0.0;
+          outv[s] = r0 + (y[s] - cl) * wb[L::SM + 56] / wb[L::SM + 57];
+        }
         if (k < ns) p2 += outv[s];
       }
       double Tout = 0.0;
