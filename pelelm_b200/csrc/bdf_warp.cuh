@@ -185,13 +185,23 @@ __device__ __noinline__ int gjinv_warp()
         if (L::PAIRS) {  // rows are 16-byte aligned and an odd number of 16-byte units apart: conflict-free pair sweeps
           const double2* rk2 = reinterpret_cast<const double2*>(rk);
           double2* row2 = reinterpret_cast<double2*>(row);
+          // next column pair loaded before this one is stored (see gjinv2_warp): same arithmetic, no load -> store -> load chain
+          double2 p = rk2[0], r = row2[0];
 #pragma unroll 2
           for (int j = 0; j < n / 2; ++j) {
-            const double2 p = rk2[j];
-            double2 r = row2[j];
+#if defined(PLM_GJPIPE) && !PLM_GJPIPE
+            const int jn = j;  // development: the unpipelined loop (loads of pair j issued in iteration j)
+            p = rk2[j];
+            r = row2[j];
+#else
+            const int jn = j + 1;  // the last iteration reads one pair past the row: the next row, or the pad behind the matrix
+#endif
+            const double2 pn = rk2[jn], rn = row2[jn];
             r.x -= p.x * f;
             r.y -= p.y * f;
             row2[j] = r;
+            p = pn;
+            r = rn;
           }
         } else {
 #pragma unroll 2
@@ -199,6 +209,191 @@ __device__ __noinline__ int gjinv_warp()
         }
       }
     }
+    __syncwarp();
+  }
+  return 0;
+}
+
+// arg-max of (v, idx) over the warp, first row winning ties, v < 0 / NaN = "no candidate" (three hardware reductions, see
+// gjinv_warp); returns warp-uniform v (-1 when no lane has a candidate) and idx.
+__device__ __forceinline__ void argmax_first(double& v, int& idx)
+{
+  const bool ok = v >= 0.0;
+  const unsigned hi = ok ? unsigned(__double2hiint(v)) + 1u : 0u;
+  const unsigned mhi = __reduce_max_sync(kFull, hi);
+  const bool c1 = ok && hi == mhi;
+  const unsigned lo = c1 ? unsigned(__double2loint(v)) : 0u;
+  const unsigned mlo = __reduce_max_sync(kFull, lo);
+  const bool win = c1 && lo == mlo;
+  const unsigned first = __reduce_min_sync(kFull, win ? unsigned(idx) : 0x7fffffffu);
+  v = __shfl_sync(kFull, v, int(first & 31u));
+  idx = (mhi == 0u) ? 0x7fffffff : int(first);
+  if (mhi == 0u) v = -1.0;
+}
+
+// The same inverse, two pivots per sweep (systems of two rows per lane, n even: dodecane_lu). Every element receives the
+// same fused multiply-adds in the same order as in gjinv_warp -- pivot k, then pivot k+1 -- so W is the same matrix (up
+// to the sign of exact zeros); what changes is the traffic: a lane's rows are read and written once per PAIR of pivots
+// (18 instead of 34 shared-memory wavefronts per 16-byte column pair) and eight independent FMAs ride on every round
+// trip. The panel work that makes this possible: after pivot row k is final, column k+1 as pivot k leaves it is
+// formed in registers (c), the second pivot is searched in it, and the two rows that swap places for pivot k+1 are
+// brought up to date with pivot k on their own (lane = column) before the swap and the scaling. Row k itself, which
+// every lane reads as the first pivot row during the sweep, gets its pivot-(k+1) update after the sweep.
+template <class L>
+__device__ __noinline__ int gjinv2_warp()
+{
+  constexpr int n = L::N, ld = L::LD;
+  static_assert(L::NSLOT == 2 && L::PAIRS && n % 2 == 0 && n > 32, "two rows per lane, even order");
+  double* wb = warp_base<L>();
+  double* A = wb + L::A;
+  int* perm = reinterpret_cast<int*>(wb + L::PERM);
+  const int lane = threadIdx.x & 31;
+  const int i0 = lane, i1 = lane + 32;
+  const bool has1 = i1 < n;
+  const int i1c = has1 ? i1 : n - 1;  // clamped for addressing; its results are never stored
+  perm[i0] = i0;
+  if (has1) perm[i1] = i1;
+  __syncwarp();
+  double* row0 = A + i0 * ld;
+  double* row1 = A + i1c * ld;
+#pragma unroll 1
+  for (int k = 0; k < n; k += 2) {
+    const int k1 = k + 1;
+    // ---- pivot k: search, swap, scale (as gjinv_warp)
+    double v = -1.0;
+    int idx = 0x7fffffff;
+    if (i0 >= k) {
+      v = fabs(row0[k]);
+      idx = i0;
+      if (!(v > -1.0)) {  // NaN: never larger in the reference's comparison
+        v = -1.0;
+        idx = 0x7fffffff;
+      }
+    }
+    if (has1 && i1 >= k) {
+      const double a = fabs(row1[k]);
+      if (a > v) {
+        v = a;
+        idx = i1;
+      }
+    }
+    argmax_first(v, idx);
+    if (!(v > 0.0)) return k + 1;
+    const int l = idx;
+    const double pivinv = 1.0 / A[l * ld + k];
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) {
+      const double t = A[l * ld + j];
+      if (l != k) A[l * ld + j] = A[k * ld + j];
+      A[k * ld + j] = (j == k) ? pivinv : t * pivinv;
+    }
+    if (lane == 0 && l != k) {
+      const int t = perm[l];
+      perm[l] = perm[k];
+      perm[k] = t;
+    }
+    __syncwarp();
+    const double* rk = A + k * ld;
+    double* rq = A + k1 * ld;
+    // ---- multipliers of pivot k and column k+1 as pivot k leaves it
+    const double rk1 = rk[k1];
+    double fA0 = (i0 != k) ? row0[k] : 0.0;
+    double fA1 = (has1 && i1 != k) ? row1[k] : 0.0;
+    double fB0 = (i0 != k) ? fma(-rk1, fA0, row0[k1]) : rk1;
+    double fB1 = (i1 != k) ? fma(-rk1, fA1, row1[k1]) : rk1;
+    // ---- pivot k+1: search in that column
+    v = -1.0;
+    idx = 0x7fffffff;
+    if (i0 >= k1) {
+      v = fabs(fB0);
+      idx = i0;
+      if (!(v > -1.0)) {
+        v = -1.0;
+        idx = 0x7fffffff;
+      }
+    }
+    if (has1 && i1 >= k1) {
+      const double a = fabs(fB1);
+      if (a > v) {
+        v = a;
+        idx = i1;
+      }
+    }
+    argmax_first(v, idx);
+    if (!(v > 0.0)) return k1 + 1;
+    const int l1 = idx;
+    const double cl1 = __shfl_sync(kFull, l1 < 32 ? fB0 : fB1, l1 & 31), fl1 = __shfl_sync(kFull, l1 < 32 ? fA0 : fA1, l1 & 31);
+    const double ck1 = __shfl_sync(kFull, k1 < 32 ? fB0 : fB1, k1 & 31), fk1 = __shfl_sync(kFull, k1 < 32 ? fA0 : fA1, k1 & 31);
+    const double pivinv1 = 1.0 / cl1;
+    __syncwarp();
+    // ---- rows l1 and k+1 brought up to date with pivot k, swapped, the new row k+1 scaled (lane = column)
+    for (int j = lane; j < n; j += 32) {
+      const double r = rk[j];
+      const double tl = fma(-r, fl1, (j == k) ? 0.0 : A[l1 * ld + j]);
+      if (l1 != k1) A[l1 * ld + j] = fma(-r, fk1, (j == k) ? 0.0 : rq[j]);
+      rq[j] = (j == k1) ? pivinv1 : tl * pivinv1;
+    }
+    if (lane == 0 && l1 != k1) {
+      const int t = perm[l1];
+      perm[l1] = perm[k1];
+      perm[k1] = t;
+    }
+    // ---- what is left for the sweep, per row: pivot k (fA) then pivot k+1 (fB)
+    //   row k      : nothing here (its pivot-(k+1) update follows the sweep: every lane reads it meanwhile)
+    //   row k+1    : the second pivot row, final
+    //   row l1     : holds the old row k+1, already through pivot k; multiplier of pivot k+1 = its column-(k+1) entry ck1
+    bool on0 = i0 != k && i0 != k1, on1 = has1 && i1 != k && i1 != k1;
+    if (l1 != k1) {
+      if (i0 == l1) {
+        fA0 = 0.0;
+        fB0 = ck1;
+      } else if (on0) {
+        row0[k] = 0.0;
+      }
+      if (i1 == l1) {
+        fA1 = 0.0;
+        fB1 = ck1;
+      } else if (on1) {
+        row1[k] = 0.0;
+      }
+    } else {
+      if (on0) row0[k] = 0.0;
+      if (on1) row1[k] = 0.0;
+    }
+    __syncwarp();
+    {
+      // Software-pipelined by hand: the operands of column pair j+1 are loaded before pair j is stored. The compiler keeps
+      // shared-memory loads behind earlier stores it cannot prove disjoint (everything here derives from one base
+      // pointer), which left every iteration a full load -> FMA -> store round trip (the short-scoreboard stalls of the
+      // capture). No lane stores into a row it reads as a pivot row (rows k and k+1 are "off"), and a lane's own rows
+      // are only its own, so the early loads are safe.
+      const double2* p2 = reinterpret_cast<const double2*>(rk);
+      const double2* q2 = reinterpret_cast<const double2*>(rq);
+      double2* r0 = reinterpret_cast<double2*>(row0);
+      double2* r1 = reinterpret_cast<double2*>(row1);
+      double2 p = p2[0], q = q2[0], a = r0[0], b = r1[0];
+#pragma unroll 3
+      for (int j = 0; j < n / 2; ++j) {
+        const int jn = j + 1;  // the last iteration reads one pair past the row: the next row, or the pad behind the matrix
+        const double2 pn = p2[jn], qn = q2[jn], an = r0[jn], bn = r1[jn];
+        a.x = fma(-q.x, fB0, fma(-p.x, fA0, a.x));
+        a.y = fma(-q.y, fB0, fma(-p.y, fA0, a.y));
+        b.x = fma(-q.x, fB1, fma(-p.x, fA1, b.x));
+        b.y = fma(-q.y, fB1, fma(-p.y, fA1, b.y));
+        if (on0) r0[j] = a;
+        if (on1) r1[j] = b;
+        p = pn;
+        q = qn;
+        a = an;
+        b = bn;
+      }
+    }
+    // column k+1 of the swept rows: zeroed before pivot k+1 acts on it (what the sweep left there is overwritten)
+    if (on0) row0[k1] = fma(-pivinv1, fB0, 0.0);
+    if (on1) row1[k1] = fma(-pivinv1, fB1, 0.0);
+    __syncwarp();
+    // ---- row k through pivot k+1 (multiplier = its column-(k+1) entry rk1)
+    for (int j = lane; j < n; j += 32) A[k * ld + j] = fma(-rq[j], rk1, (j == k1) ? 0.0 : A[k * ld + j]);
     __syncwarp();
   }
   return 0;
@@ -441,7 +636,13 @@ struct BdfWarp {
       A[e] = a;
     }
     __syncwarp();
+#if !defined(PLM_GJ2) || PLM_GJ2
+    int ier;
+    if constexpr (NSLOT == 2 && L::PAIRS) ier = gjinv2_warp<L>();
+    else ier = gjinv_warp<L>();
+#else
     const int ier = gjinv_warp<L>();
+#endif
     nsetups++;
     gamrat = 1.0;
     gammap = gamma;
