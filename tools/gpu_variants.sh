@@ -10,6 +10,7 @@ for v in $variants; do
       LiDryer) args="--mech LiDryer --cells 262144";;
       rk64) args="--mech LiDryer --integrator ReactorRK64 --cells 131072";;
       dodecane_lu) args="--mech dodecane_lu --cells 16384 --box-cells 16384";;
+      dodecane64k) args="--mech dodecane_lu --cells 65536 --box-cells 16384";;
       loose) args="--cells 1048576 --rtol 1e-6 --max-order 4";;
     esac
     r=$(PLM_LIBPATH=$PWD/$lib timeout 300 python bench.py $args --steps 2 --warmup 2 --no-cpu-baseline --e2e-steps 0 2>&1 | tail -1)
