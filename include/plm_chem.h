@@ -113,6 +113,13 @@ int  plm_eval_jac(plm_reactor*, int ncells, const double* y, double* J, void* cu
 int  plm_box_costs(const double* FC, const int64_t* box_offsets, int nboxes, int64_t* costs, void* cuda_stream);
 int  plm_knapsack(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack,
                   int nmax, int* rank_of_box, double* efficiency);
+/* The same with the reference's default sort = true (AMReX_DistributionMapping.H:139-143): the i-th heaviest bucket (or, with
+ * at most one box per rank, box i) goes to rank_order[i]; rank_order = plm_least_used_ranks of the kilobytes each rank holds
+ * in FABs (DistributionMapping::LeastUsedCPUs :191-235, one all-gather of a long per rank; KnapSackDoIt :718-844,
+ * RoundRobinDoIt :365-447). plm_knapsack is the rank_order = identity case (all ranks equally loaded). */
+int  plm_knapsack_ordered(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack,
+                          int nmax, const int* rank_order, int* rank_of_box, double* efficiency);
+int  plm_least_used_ranks(const int64_t* kbytes, int nranks, int* rank_order);
 
 /* ---- measurement: register-resident DFMA throughput of the current device in TFLOP/s (the FP64 SIMT roofline
  *      denominator; no reference counterpart) ---- */

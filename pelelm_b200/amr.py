@@ -205,11 +205,12 @@ def average_down(L: Level, fine: Level, key_fine="I_R_old", key_crse="I_R", rati
 
 
 def advance_chemistry_level(L: Level, dt, advance_box, fine: Level | None = None, avg_down_chem=True, use_knapsack=True,
-                            cost_fn=None, group=None, device=None, wait=None):
+                            cost_fn=None, group=None, device=None, wait=None, rank_order=None):
     """One PeleLM::advance_chemistry of level L (steps 1-5 of the module docstring).
 
     advance_box(box: dict, shape, dt, slot) advances box["S"] in place, writes box["I_R"] and box["FC"]; `wait()` (if
-    given) blocks until every advance_box call has finished (asynchronous launches on the GPU).
+    given) blocks until every advance_box call has finished (asynchronous launches on the GPU); rank_order =
+    pelelm_b200.dist.least_used_ranks(...) hands the heaviest bucket to the least-used rank (the reference's sort = true).
     Returns {"chem_owner", "costs", "efficiency", "moved"}."""
     rk, nr = _rank(group), _world(group)
     # the new time level starts: what was new becomes old (the state swap of the time step)
@@ -217,7 +218,7 @@ def advance_chemistry_level(L: Level, dt, advance_box, fine: Level | None = None
         bx["I_R_old"], bx["I_R"] = bx["I_R"], bx["I_R_old"]
     costs = pd.gather_box_costs(local_box_costs(L, cost_fn), L.owner, group=group)
     if use_knapsack:
-        chem_owner, eff = pd.func_count_dm(costs, nr, default_owner=L.owner)
+        chem_owner, eff = pd.func_count_dm(costs, nr, default_owner=L.owner, rank_order=rank_order)
     else:
         chem_owner, eff = L.owner.copy(), None
     chem_owner = np.asarray(chem_owner, dtype=np.int32)

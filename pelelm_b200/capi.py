@@ -42,7 +42,8 @@ class Stats(C.Structure):
 EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals", "plm_react_box", "plm_react_flat",
            "plm_advance_chemistry_box", "plm_reaction_rate_rhoY",
            "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
-           "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_measure_fp64_peak", "plm_species_name"]
+           "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_knapsack_ordered", "plm_least_used_ranks",
+           "plm_measure_fp64_peak", "plm_species_name"]
 
 _lib = None
 
@@ -77,6 +78,8 @@ def load():
     L.plm_eval_jac.argtypes = [vp, C.c_int, vp, vp, vp]
     L.plm_box_costs.argtypes = [vp, vp, C.c_int, vp, vp]
     L.plm_knapsack.argtypes = [C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_ip, c_dp]
+    L.plm_knapsack_ordered.argtypes = [C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_ip, c_ip, c_dp]
+    L.plm_least_used_ranks.argtypes = [C.POINTER(C.c_int64), C.c_int, c_ip]
     L.plm_measure_fp64_peak.argtypes = [c_dp, vp]
     _lib = L
     return L
@@ -94,17 +97,36 @@ def _ptr(x):
     return x.data_ptr()  # torch tensor
 
 
-def knapsack(wgts, nranks, max_efficiency=0.9, do_full=True, nmax=2 ** 31 - 1):
-    """DistributionMapping::KnapSackProcessorMap on a cost vector (host only; needs no GPU)."""
+def knapsack(wgts, nranks, max_efficiency=0.9, do_full=True, nmax=2 ** 31 - 1, rank_order=None):
+    """DistributionMapping::KnapSackProcessorMap on a cost vector (host only; needs no GPU). rank_order (a permutation of
+    the ranks, e.g. least_used_ranks(...)) is the reference's sort = true: the i-th heaviest bucket goes to rank_order[i]."""
     L = load()
     w = (C.c_int64 * len(wgts))(*[int(v) for v in wgts])
     out = np.zeros(len(wgts), dtype=np.int32)
     eff = C.c_double(0)
-    rc = L.plm_knapsack(w, len(wgts), nranks, max_efficiency, int(do_full), nmax,
-                        out.ctypes.data_as(c_ip), C.cast(C.byref(eff), c_dp))
+    if rank_order is None:
+        rc = L.plm_knapsack(w, len(wgts), nranks, max_efficiency, int(do_full), nmax,
+                            out.ctypes.data_as(c_ip), C.cast(C.byref(eff), c_dp))
+    else:
+        ro = np.ascontiguousarray(rank_order, dtype=np.int32)
+        if ro.size != nranks:
+            raise PlmError("rank_order must list every rank once")
+        rc = L.plm_knapsack_ordered(w, len(wgts), nranks, max_efficiency, int(do_full), nmax, ro.ctypes.data_as(c_ip),
+                                    out.ctypes.data_as(c_ip), C.cast(C.byref(eff), c_dp))
     if rc != 0:
         raise PlmError("plm_knapsack failed")
     return out, eff.value
+
+
+def least_used_ranks(kbytes):
+    """DistributionMapping::LeastUsedCPUs: ranks by ascending kilobytes held (stable)."""
+    L = load()
+    n = len(kbytes)
+    kb = (C.c_int64 * n)(*[int(v) for v in kbytes])
+    out = np.zeros(n, dtype=np.int32)
+    if L.plm_least_used_ranks(kb, n, out.ctypes.data_as(c_ip)) != 0:
+        raise PlmError("plm_least_used_ranks failed")
+    return out
 
 
 def measure_fp64_peak() -> float:

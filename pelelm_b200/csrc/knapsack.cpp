@@ -36,12 +36,21 @@ struct BucketRef {
 
 }  // namespace
 
-extern "C" int plm_knapsack(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack,
-                            int nmax, int* rank_of_box, double* efficiency)
+// ord[i] = the rank that takes the i-th bucket (heaviest first) or, with at most one box per rank, box i (round robin):
+// identity, or the ranks by ascending FAB bytes (DistributionMapping::LeastUsedCPUs, the reference's sort = true default)
+static int knapsack_core(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack, int nmax,
+                         const int* ord, int* rank_of_box, double* efficiency)
 {
   if (!wgts || !rank_of_box || nboxes < 0 || nranks < 1) return PLM_ERR_ARG;
-  if (nboxes <= nranks || nranks < 2) {  // RoundRobinProcessorMap
-    for (int i = 0; i < nboxes; ++i) rank_of_box[i] = i % nranks;
+  if (ord) {  // must be a permutation of the ranks
+    std::vector<char> seen(nranks, 0);
+    for (int i = 0; i < nranks; ++i) {
+      if (ord[i] < 0 || ord[i] >= nranks || seen[ord[i]]) return PLM_ERR_ARG;
+      seen[ord[i]] = 1;
+    }
+  }
+  if (nboxes <= nranks || nranks < 2) {  // RoundRobinProcessorMap -> RoundRobinDoIt (:365-447): box i -> ord[i % nranks]
+    for (int i = 0; i < nboxes; ++i) rank_of_box[i] = ord ? ord[i % nranks] : i % nranks;
     if (efficiency) *efficiency = 1.0;
     return PLM_OK;
   }
@@ -123,12 +132,35 @@ extern "C" int plm_knapsack(const int64_t* wgts, int nboxes, int nranks, double 
       if (!swapped) break;
     }
   }
-  // heaviest bucket -> rank 0, next -> rank 1, ... (stable on ties)
+  // heaviest bucket -> ord[0], next -> ord[1], ... (stable on ties; KnapSackDoIt :760-815)
   std::vector<int> idx(v.size());
   std::iota(idx.begin(), idx.end(), 0);
   std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return v[a].w > v[b].w; });
-  for (size_t rank = 0; rank < idx.size(); ++rank)
-    for (const Item& it : bk[v[idx[rank]].id].items) rank_of_box[it.box] = int(rank);
+  for (size_t i = 0; i < idx.size(); ++i)
+    for (const Item& it : bk[v[idx[i]].id].items) rank_of_box[it.box] = ord ? ord[i] : int(i);
   if (efficiency) *efficiency = eff;
+  return PLM_OK;
+}
+
+extern "C" int plm_knapsack(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack,
+                            int nmax, int* rank_of_box, double* efficiency)
+{
+  return knapsack_core(wgts, nboxes, nranks, max_efficiency, do_full_knapsack, nmax, nullptr, rank_of_box, efficiency);
+}
+
+extern "C" int plm_knapsack_ordered(const int64_t* wgts, int nboxes, int nranks, double max_efficiency, int do_full_knapsack,
+                                    int nmax, const int* rank_order, int* rank_of_box, double* efficiency)
+{
+  if (!rank_order) return PLM_ERR_ARG;
+  return knapsack_core(wgts, nboxes, nranks, max_efficiency, do_full_knapsack, nmax, rank_order, rank_of_box, efficiency);
+}
+
+// DistributionMapping::LeastUsedCPUs (AMReX_DistributionMapping.cpp:191-235): ranks by ascending kilobytes held in FABs,
+// rank order kept among equals (std::stable_sort with LIpairLT)
+extern "C" int plm_least_used_ranks(const int64_t* kbytes, int nranks, int* rank_order)
+{
+  if (!kbytes || !rank_order || nranks < 1) return PLM_ERR_ARG;
+  std::iota(rank_order, rank_order + nranks, 0);
+  std::stable_sort(rank_order, rank_order + nranks, [&](int a, int b) { return kbytes[a] < kbytes[b]; });
   return PLM_OK;
 }

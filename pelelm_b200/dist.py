@@ -89,14 +89,30 @@ def gather_box_costs(local_costs, owner_of_box, group=None):
     return v.cpu().numpy()
 
 
-def func_count_dm(costs, nranks, default_owner=None):
-    """getFuncCountDM's decision: FC all zero -> keep the default mapping (PeleLM.cpp:5545-5549), else knapsack."""
+def func_count_dm(costs, nranks, default_owner=None, rank_order=None):
+    """getFuncCountDM's decision: FC all zero -> keep the default mapping (PeleLM.cpp:5545-5549), else knapsack.
+    rank_order = least_used_ranks(...) gives the reference's sort = true bucket -> rank assignment; None = identity
+    (every rank holds the same amount of state, as in the synthetic configurations)."""
     costs = np.asarray(costs, dtype=np.int64)
     if costs.size == 0 or costs.max() <= 0:
         if default_owner is not None:
             return np.asarray(default_owner, dtype=np.int32), 1.0
         return (np.arange(costs.size) % nranks).astype(np.int32), 1.0
-    return capi.knapsack(costs, nranks)
+    return capi.knapsack(costs, nranks, rank_order=rank_order)
+
+
+def least_used_ranks(local_kbytes, group=None):
+    """DistributionMapping::LeastUsedCPUs (AMReX_DistributionMapping.cpp:191-235): one all-gather of the kilobytes each rank
+    holds (the reference counts FAB bytes; a GPU rank passes torch.cuda.memory_allocated() // 1024), then the ranks by
+    ascending load, equal on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return np.zeros(1, dtype=np.int32)
+    ws = dist.get_world_size(group)
+    dev = _device()
+    mine = torch.tensor([int(local_kbytes)], dtype=torch.int64, device=dev)
+    allv = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(ws)]
+    dist.all_gather(allv, mine, group=group)
+    return capi.least_used_ranks([int(v.item()) for v in allv])
 
 
 def reduce_stats(stats: dict, group=None):

@@ -122,3 +122,31 @@ def test_reference_factory_knows_b200_reactors():
     assert r.returncode != 0
     assert "Creating ReactorBase instance: ReactorRK64B200" in r.stdout
     assert "no CUDA device" in r.stderr
+
+
+def test_knapsack_ordered_is_the_sort_true_mapping(plm_lib):
+    """plm_knapsack_ordered / plm_least_used_ranks: KnapSackDoIt's bucket -> rank step with the reference's default
+    sort = true (AMReX_DistributionMapping.cpp:760-815): the i-th heaviest bucket goes to the i-th least-used rank
+    (LeastUsedCPUs :191-235, stable on ties); with at most one box per rank, box i goes to ord[i % nranks]
+    (RoundRobinDoIt :365-447).  The partition itself is the one already pinned against AMReX's knapsack()."""
+    from pelelm_b200 import capi
+    rng = np.random.default_rng(5)
+    kb = [700, 100, 100, 900, 50, 100, 800, 0]
+    ord8 = capi.least_used_ranks(kb)
+    assert ord8.tolist() == [7, 4, 1, 2, 5, 0, 6, 3]          # ascending load, rank order kept among equals
+    for nb, nr, order in [(64, 2, np.array([1, 0])), (200, 8, ord8), (513, 4, np.array([2, 0, 3, 1])), (8, 8, ord8), (5, 8, ord8)]:
+        w = rng.integers(1, 10 ** 6, nb)
+        a, ea = capi.knapsack(w, nr)                           # identity order: bucket i -> rank i (heaviest first)
+        b, eb = capi.knapsack(w, nr, rank_order=order)
+        assert ea == eb
+        assert np.array_equal(b, np.asarray(order)[a])         # same buckets, renamed through the order
+        if nb > nr:
+            load = np.bincount(b, weights=w, minlength=nr)
+            assert np.all(np.diff(load[np.asarray(order)]) <= 0)   # heaviest bucket sits on the least-used rank
+    # identity order reproduces plm_knapsack exactly; a non-permutation is rejected
+    w = rng.integers(1, 1000, 40)
+    assert np.array_equal(capi.knapsack(w, 4)[0], capi.knapsack(w, 4, rank_order=np.arange(4))[0])
+    with pytest.raises(capi.PlmError):
+        capi.knapsack(w, 4, rank_order=np.array([0, 1, 1, 3]))
+    with pytest.raises(capi.PlmError):
+        capi.knapsack(w, 4, rank_order=np.array([0, 1, 2]))

@@ -50,6 +50,11 @@ def _worker(rank, ws, port, q):
     for b, bx in moved.items():
         assert torch.all(bx["S"] == float(b)) and torch.all(bx["F"] == -float(b)) and torch.all(bx["m"] == int(b))
         assert bx["m"].dtype == torch.int32 and tuple(bx["S"].shape) == (2, 5)
+    # LeastUsedCPUs: one all-gather of the kilobytes each rank holds; the heaviest bucket goes to the least-used rank
+    order = pd.least_used_ranks(5000 if rank == 0 else 100)
+    assert order.tolist() == [1, 0]
+    own2, eff2 = pd.func_count_dm(full, ws, rank_order=order)
+    assert np.array_equal(own2, 1 - new_owner) and eff2 == eff
     st = pd.reduce_stats({"ncells": 10 + rank, "nfe": 100 * (rank + 1), "max_fc": 5 + rank, "min_fc": 3 - rank,
                           "kernel_ms": 1.0 + rank})
     q.put((rank, new_owner.tolist(), eff, st))
