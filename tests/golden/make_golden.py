@@ -153,6 +153,54 @@ def etype(mech: str):
     print(mech, "e-reactor golden written:", len(out), "arrays")
 
 
+def flamesheet(mech: str):
+    """tests/golden/<mech>_flamesheet.npz (BASELINE.json configs[0], Exec/RegTests/FlameSheet): states sampled across the
+    premixed-flame profile the FlameSheet case is initialised from (`<mech>_pmf.dat` next to `inputs.2d-regt`: position,
+    T, u, rho, mole fractions; read as pelelm_prob.H / PMF.H do, X -> Y, p = 1 atm), advanced by the reference's
+    ReactorCvode with the chemistry settings of `inputs.2d-regt` (rtol 1e-6, atol 1e-5 x typical values, max_order 4,
+    denseAJ_direct) over dt = 1e-5 s, with a smooth advection-diffusion-like forcing of 2 % of the state per dt."""
+    from oracle.pyoracle import Ref
+    from pelelm_b200 import synth
+    pmf = {"drm19": "drm19_pmf.dat", "dodecane_lu": "dodecaneLu_pmf.dat"}[mech]
+    path = os.path.join("/root/reference/Exec/RegTests/FlameSheet", pmf)
+    names = open(path).readline().split('"')[1::2]
+    tab = np.loadtxt(path, skiprows=2)
+    R = Ref(mech)
+    m = synth.mech(mech)
+    nc = {"drm19": 64, "dodecane_lu": 8}[mech]
+    # rows spread evenly in temperature from the cold to the hot boundary: the whole reaction zone is sampled
+    Tcol = tab[:, 1]
+    want = np.linspace(Tcol.min() + 2.0, Tcol.max() - 2.0, nc)
+    rows = np.array([int(np.argmin(np.abs(Tcol - t))) for t in want])
+    X = np.zeros((nc, m.ns))
+    for j, nm in enumerate(names[4:]):
+        if nm in R.species:
+            X[:, R.species.index(nm)] = np.maximum(tab[rows, 4 + j], 0.0)
+    X /= X.sum(1, keepdims=True)
+    Y = X * m.mw[None, :]
+    Y /= Y.sum(1, keepdims=True)
+    T = Tcol[rows].copy()
+    rho, h = R.pty2rh(1013250.0, T, np.ascontiguousarray(Y))
+    rY = np.ascontiguousarray((Y * rho[:, None]).T)
+    rE = rho * h
+    s = np.linspace(0.0, 1.0, nc)
+    src = 2e-2 * np.sin(2 * np.pi * (s[None, :] + np.arange(m.ns)[:, None] / m.ns)) * rY / DT
+    src -= rY / rY.sum(0, keepdims=True) * src.sum(0, keepdims=True)      # no net mass source
+    esrc = 2e-2 * np.cos(2 * np.pi * s) * np.abs(rE) / DT
+    b = {"rY": rY, "rYsrc": np.ascontiguousarray(src), "T": T, "rE": rE, "rEsrc": esrc, "mask": np.ones(nc, dtype=np.int32)}
+    ikw = dict(rtol=1e-6, atol=1e-5, max_order=4)
+    R.init(integrator="ReactorCvode", **ikw)
+    tv = typ_vals(b)
+    R.set_typ_vals(tv)
+    out = {"typ": tv, "rows": rows}
+    rY2, T2, rE2, FC = R.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT)
+    for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask"):
+        out["in_" + k] = b[k]
+    out["rY"], out["T"], out["rE"], out["FC"] = rY2, T2, rE2, FC
+    np.savez_compressed(os.path.join(HERE, mech + "_flamesheet.npz"), **out)
+    print(mech, "flamesheet golden written: T %.0f..%.0f K, FC %d..%d" % (T.min(), T.max(), FC.min(), FC.max()))
+
+
 def knap():
     """KnapSackProcessorMap buckets from the reference's own knapsack() (any libref works)."""
     import ctypes as C
@@ -197,6 +245,11 @@ def vismf():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "vismf":
         vismf()
+    elif len(sys.argv) > 2 and sys.argv[1] == "flamesheet":
+        flamesheet(sys.argv[2])
+    elif len(sys.argv) > 1 and sys.argv[1] == "flamesheet":
+        for m in ("drm19", "dodecane_lu"):
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "flamesheet", m])
     elif len(sys.argv) > 2 and sys.argv[1] == "etype":
         etype(sys.argv[2])
     elif len(sys.argv) > 1 and sys.argv[1] == "etype":

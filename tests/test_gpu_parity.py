@@ -456,3 +456,21 @@ def test_amr_levels_vs_port(capi, port_lib):
             unc = ~cov.ravel()
             sc = 1e-6 * np.abs(r["I_R"]) + 1e-6 * np.abs(r["I_R"]).max(1, keepdims=True) + 1e-7 / DT
             assert (np.abs(g["I_R"] - r["I_R"]) <= sc)[:, unc].all(), (l, b)
+
+
+@pytest.mark.parametrize("mech", ["drm19", "dodecane_lu"])
+def test_flamesheet_profile_vs_reference(capi, mech):
+    """BASELINE.json configs[0]: states across the FlameSheet case's premixed-flame profile with the chemistry settings of
+    Exec/RegTests/FlameSheet/inputs.2d-regt (rtol 1e-6, atol 1e-5 x typical values, order 4), CUDA path against the
+    reference's own output (tests/golden/<mech>_flamesheet.npz, make_golden.py::flamesheet)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, mech + "_flamesheet.npz"))
+    ikw = dict(rtol=1e-6, atol=1e-5, max_order=4)
+    b = {k: g["in_" + k] for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask")}
+    got, st, status = _gpu_react(capi, mech, "ReactorCvode", ikw, b, g["typ"])
+    ref = (g["rY"], g["T"], g["rE"], g["FC"])
+    small = mech != "dodecane_lu"
+    check_state(got, ref, ikw["atol"] * g["typ"][:-1, None], tag=mech + "/flamesheet", rtol=100 * ikw["rtol"],
+                fc_equal_min=0.9 if small else None, fc_rel=0.05 if small else 0.15)
+    assert not status.any() and st["nskipped"] == 0

@@ -1,9 +1,11 @@
 """The oracle port (oracle/port/*.c) pinned against the UNMODIFIED reference through the golden fixtures
 (tests/golden/*.npz, written by tests/golden/make_golden.py from oracle/_ref/libref_<mech>.so)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import MECHS, golden, golden_plm, golden_e, check_state, scaled_err
+from conftest import MECHS, GOLDEN, golden, golden_plm, golden_e, check_state, scaled_err
 from golden.make_golden import CASES, DT
 
 
@@ -140,3 +142,19 @@ def test_port_internal_energy_reactor_vs_reference(port_lib, mech):
         ref = (g[case + "/rY"], g[case + "/T"], g[case + "/rE"], g[case + "/FC"])
         check_state(got, ref, 1e-10, tag="%s/%s" % (mech, case), rtol=1e-6, fc_equal_min=0.9 if small else None,
                     fc_rel=0.05 if small else 0.2)
+
+
+@pytest.mark.parametrize("mech", ["drm19", "dodecane_lu"])
+def test_port_flamesheet_profile_vs_reference(port_lib, mech):
+    """BASELINE.json configs[0]: states across the FlameSheet case's premixed-flame profile, chemistry settings of
+    Exec/RegTests/FlameSheet/inputs.2d-regt (tests/golden/make_golden.py::flamesheet), port against the reference."""
+    g = np.load(os.path.join(GOLDEN, mech + "_flamesheet.npz"))
+    ikw = dict(rtol=1e-6, atol=1e-5, max_order=4)
+    P = _port(port_lib, mech, "ReactorCvode", ikw)
+    P.set_typ_vals(g["typ"])
+    out = P.react_soa(g["in_rY"], g["in_rYsrc"], g["in_T"], g["in_rE"], g["in_rEsrc"], g["in_mask"], DT)
+    ref = (g["rY"], g["T"], g["rE"], g["FC"])
+    small = mech != "dodecane_lu"
+    check_state(out, ref, ikw["atol"] * g["typ"][:-1, None], tag=mech + "/flamesheet", rtol=100 * ikw["rtol"],
+                fc_equal_min=0.9 if small else None, fc_rel=0.05 if small else 0.15)
+    assert g["in_T"].min() < 400.0 and g["in_T"].max() > 1500.0 and g["FC"].max() > 5 * g["FC"].min()   # cold gas to burnt gas
