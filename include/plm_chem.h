@@ -88,6 +88,12 @@ int  plm_advance_chemistry_box(plm_reactor*, const int lo[3], const int hi[3], p
 int  plm_reaction_rate_rhoY(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
                             plm_a4i mask, plm_a4d rhoYdot, void* cuda_stream);
 
+/* Which kernel family the react / eval calls of this reactor run (no reference counterpart; the parity tests use it to hold
+ * both families to the same fixtures): 0 = automatic (default: lane = cell kernels -- one thread per cell, straight-line
+ * generated mechanism code -- where they cover the request: LiDryer / drm19 with ReactorRK64 or ReactorCvode +
+ * denseAJ_direct on the enthalpy reactor; warp-per-cell kernels otherwise), 1 = warp-per-cell kernels, 2 = lane = cell
+ * kernels (react calls fail with PLM_ERR_ARG when they do not cover the request). */
+int  plm_reactor_set_path(plm_reactor*, int path);
 /* waits for every outstanding call of this reactor, then returns and clears the accumulated counters */
 int  plm_reactor_stats(plm_reactor*, plm_stats* out);
 /* status word per cell of the last call, in box order (device or host destination) */

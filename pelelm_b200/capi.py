@@ -43,7 +43,7 @@ EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals",
            "plm_advance_chemistry_box", "plm_reaction_rate_rhoY",
            "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
            "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_knapsack_ordered", "plm_least_used_ranks",
-           "plm_measure_fp64_peak", "plm_species_name"]
+           "plm_measure_fp64_peak", "plm_species_name", "plm_reactor_set_path"]
 
 _lib = None
 
@@ -81,6 +81,7 @@ def load():
     L.plm_knapsack_ordered.argtypes = [C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_ip, c_ip, c_dp]
     L.plm_least_used_ranks.argtypes = [C.POINTER(C.c_int64), C.c_int, c_ip]
     L.plm_measure_fp64_peak.argtypes = [c_dp, vp]
+    L.plm_reactor_set_path.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -173,6 +174,12 @@ class Reactor:
              solve_type="denseAJ_direct", rk64=(10, 5, 500)):
         self._chk(self.L.plm_reactor_init(self.h, reactor_type, rtol, atol, max_order, max_nls_iters,
                                           clean_init_massfrac, solve_type.encode(), *rk64))
+        return self
+
+    def set_path(self, path):
+        """kernel family: 0 / "auto", 1 / "warp" (one warp per cell), 2 / "lane" (one thread per cell)"""
+        path = {"auto": 0, "warp": 1, "lane": 2}.get(path, path)
+        self._chk(self.L.plm_reactor_set_path(self.h, int(path)))
         return self
 
     def set_typ_vals_ode(self, typ):

@@ -77,6 +77,7 @@ constexpr int kStatWords = 16;
 struct CallSlot {
   DevBuf status;   // int per cell
   DevBuf jglobal;  // saved Jacobians when they do not fit in shared memory
+  DevBuf lanews;   // lane = cell path: per-cell vectors and matrices of every resident lane
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool used = false;
   int64_t ncells = 0;
@@ -101,7 +102,16 @@ struct plm_reactor {
   // cached launch configuration
   plm::LaunchCfg cfg{};
   int cfg_qmax = -1;
+  int path = 0;  // 0: automatic, 1: warp-per-cell kernels, 2: lane = cell kernels (plm_reactor_set_path)
 };
+
+namespace {
+bool use_lane(const plm_reactor* r)
+{
+  if (r->path == 1) return false;
+  return plm::lane_supported(r->mech.h, r->integ, r->opts);
+}
+}  // namespace
 
 extern "C" {
 
@@ -235,7 +245,9 @@ int configure(plm_reactor* r)
 // calls issued on different streams may overlap.
 int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
 {
-  int rc = configure(r);
+  const bool lane = use_lane(r);
+  if (r->path == 2 && !lane) return fail(PLM_ERR_ARG, "the lane = cell kernels do not cover this mechanism / integrator / option set");
+  int rc = lane ? PLM_OK : configure(r);
   if (rc != PLM_OK) return rc;
   const plm::DevMech& m = r->mech.h;
   const int si = r->next_slot;
@@ -248,6 +260,21 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
     sl.used = false;
   }
   if (sl.status.ensure(std::max<int64_t>(a.ncells, 1) * sizeof(int)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+  auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
+  if (lane) {  // one thread per cell: two CTAs of 128 threads per SM, every lane pulls its own cells from the queue
+    const int threads = plm::lane_threads();
+    const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(2 * r->num_sms, (a.ncells + threads - 1) / threads)));
+    if (sl.lanews.ensure(plm::lane_ws_bytes(m, r->integ, r->opts.qmax, blocks)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+    PLM_CUDA(cudaMemsetAsync(ctrl + si, 0, sizeof(unsigned long long), stream));
+    PLM_CUDA(cudaEventRecord(sl.ev0, stream));
+    PLM_CUDA(plm::launch_lane_react(m, r->opts, a, r->integ, blocks, ctrl + si, ctrl + kSlots, static_cast<int*>(sl.status.p),
+                                    static_cast<double*>(sl.lanews.p), stream));
+    PLM_CUDA(cudaEventRecord(sl.ev1, stream));
+    sl.used = true;
+    sl.ncells = a.ncells;
+    r->last_slot = si;
+    return PLM_OK;
+  }
   plm::LaunchCfg cfg = r->cfg;
   const int64_t warps_needed = (a.ncells + plm::kCellsPerGrab - 1) / plm::kCellsPerGrab;
   const int wpb = cfg.threads / 32;
@@ -256,7 +283,6 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
     const size_t nw = size_t(r->cfg.blocks) * wpb;
     if (sl.jglobal.ensure(nw * plm::react_jsave_doubles(m) * sizeof(double)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
   }
-  auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
   PLM_CUDA(cudaMemsetAsync(ctrl + si, 0, sizeof(unsigned long long), stream));
   PLM_CUDA(cudaEventRecord(sl.ev0, stream));
   PLM_CUDA(plm::launch_react(m, r->mech.d, r->opts, a, cfg, r->integ, ctrl + si, ctrl + kSlots,
@@ -474,6 +500,14 @@ int plm_react_flat(plm_reactor* r, double* rY, double* rYsrc, double* rX, double
   return PLM_OK;
 }
 
+int plm_reactor_set_path(plm_reactor* r, int path)
+{
+  if (!r) return fail(PLM_ERR_ARG, "null reactor");
+  if (path < 0 || path > 2) return fail(PLM_ERR_ARG, "path must be 0 (automatic), 1 (warp per cell) or 2 (lane = cell)");
+  r->path = path;
+  return PLM_OK;
+}
+
 int plm_reactor_stats(plm_reactor* r, plm_stats* out)
 {
   if (!r || !out) return fail(PLM_ERR_ARG, "null argument");
@@ -504,6 +538,7 @@ void plm_reactor_close(plm_reactor* r)
   for (auto& sl : r->slot) {
     sl.status.release();
     sl.jglobal.release();
+    sl.lanews.release();
     if (sl.ev0) cudaEventDestroy(sl.ev0);
     if (sl.ev1) cudaEventDestroy(sl.ev1);
   }
@@ -531,7 +566,10 @@ int plm_eval_rhs(plm_reactor* r, int ncells, double t, const double* y, const do
     if ((rc = stage_in(r->scratch[3], rYsrc, size_t(ncells) * ns, &ds, st, true))) return rc;
     if ((rc = stage_in(r->scratch[4], static_cast<double*>(nullptr), size_t(ncells) * n, &dout, st, false))) return rc;
   }
-  PLM_CUDA(plm::launch_rhs(r->mech.h, r->mech.d, ncells, t, dy, de, des, ds, dout, st));
+  if (r->path != 1 && plm::lane_supported(r->mech.h, plm::kIntegRK64, r->opts))
+    PLM_CUDA(plm::launch_lane_rhs(r->mech.h, ncells, t, dy, de, des, ds, dout, st));
+  else
+    PLM_CUDA(plm::launch_rhs(r->mech.h, r->mech.d, ncells, t, dy, de, des, ds, dout, st));
   if (!dev) PLM_CUDA(cudaMemcpyAsync(ydot, dout, size_t(ncells) * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   PLM_CUDA(cudaStreamSynchronize(st));
   return PLM_OK;
@@ -550,7 +588,10 @@ int plm_eval_jac(plm_reactor* r, int ncells, const double* y, double* J, void* c
     if ((rc = stage_in(r->scratch[0], y, size_t(ncells) * n, &dy, st, true))) return rc;
     if ((rc = stage_in(r->scratch[5], static_cast<double*>(nullptr), size_t(ncells) * n * n, &dJ, st, false))) return rc;
   }
-  PLM_CUDA(plm::launch_jac(r->mech.h, r->mech.d, ncells, dy, dJ, st));
+  if (r->path != 1 && r->mech.h.eint == 0 && plm::lane_supported(r->mech.h, plm::kIntegRK64, r->opts))
+    PLM_CUDA(plm::launch_lane_jac(r->mech.h, ncells, dy, dJ, st));
+  else
+    PLM_CUDA(plm::launch_jac(r->mech.h, r->mech.d, ncells, dy, dJ, st));
   if (!dev) PLM_CUDA(cudaMemcpyAsync(J, dJ, size_t(ncells) * n * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   PLM_CUDA(cudaStreamSynchronize(st));
   return PLM_OK;

@@ -54,6 +54,16 @@ cudaError_t launch_rhs(const DevMech& m, const DevMech* dm, int ncells, double t
 cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const double* y, double* J, cudaStream_t stream);
 // PeleLM_K.H:57-101 reactionRateRhoY over a box (MKS in, MKS out; mask < 0 => zero)
 cudaError_t launch_reaction_rate(const DevMech& m, const DevMech* dm, const BoxArgs& a, plm_a4d rhoYdot, cudaStream_t stream);
+// ---- lane = cell path (lane_kernels.cu): one thread per cell, straight-line generated mechanism code ----
+bool lane_supported(const DevMech& m, int integ, const ReactOpts& o);
+int lane_threads();
+size_t lane_ws_bytes(const DevMech& m, int integ, int qmax, int blocks);   // workspace of a launch with `blocks` CTAs
+cudaError_t launch_lane_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a, int integ, int blocks,
+                              unsigned long long* counter, unsigned long long* gstats, int* status, double* ws,
+                              cudaStream_t stream);
+cudaError_t launch_lane_rhs(const DevMech& m, int ncells, double t, const double* y, const double* rhoe, const double* rhoesrc,
+                            const double* rYsrc, double* ydot, cudaStream_t stream);
+cudaError_t launch_lane_jac(const DevMech& m, int ncells, const double* y, double* J, cudaStream_t stream);
 cudaError_t launch_dfma_peak(double* scratch, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_box_costs(const double* FC, const int64_t* off, int nboxes, long long* costs, cudaStream_t stream);
 

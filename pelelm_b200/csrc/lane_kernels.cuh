@@ -1,0 +1,223 @@
+// sm_100a kernel templates of the lane = cell path (one THREAD per cell; lane_integ.h explains the round structure).
+//
+//   lane_react_kernel<M, I, LAY, EINT>   persistent warps; every LANE pulls its own cells from the global queue, so a warp
+//                                         always carries 32 cells that are each somewhere in their own integration
+//   lane_rhs_kernel / lane_jac_kernel     one fKernelSpec / cJac per thread (parity entry points and the A/B timing of the
+//                                         straight-line mechanism code against the warp-per-cell kernels)
+//
+// Used for the mechanisms whose per-cell state is small enough to keep 32 cells per warp in flight (LiDryer, drm19) with
+// ReactorRK64 and with ReactorCvode + analytic Jacobian on the enthalpy reactor -- the configuration PeleLM runs; every
+// other flavour (dodecane_lu, difference-quotient Jacobian, internal-energy BDF) goes through the warp-per-cell kernels
+// (kernels.cu).  launch_lane_react returns cudaErrorNotSupported when the request is not covered.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+
+#include "kernels.h"
+#include "lane_cell.h"
+
+namespace plm {
+
+using namespace lane;
+
+namespace lanek {
+
+constexpr int kLaneThreads = 128;
+
+__device__ __forceinline__ int64_t lane_a4_off(const plm_a4d& a, int i, int j, int k)
+{
+  return int64_t(i - a.lo[0]) + int64_t(j - a.lo[1]) * a.jstride + int64_t(k - a.lo[2]) * a.kstride;
+}
+
+// the cell's addresses; returns the mask value (1 when there is no mask)
+template <int NS>
+__device__ __forceinline__ int lane_view(const BoxArgs& a, int64_t c, CellView& v)
+{
+  if (a.flat) {
+    v.rY = a.rY.p + c * (NS + 1); v.sY = 1;
+    v.rYsrc = a.rYsrc.p + c * NS; v.sS = 1;
+    v.T = nullptr; v.rE = a.rE.p + c; v.rEsrc = a.rEsrc.p + c; v.FC = a.FC.p + c; v.IR = nullptr; v.sI = 0;
+    return 1;
+  }
+  const int nx = a.hi[0] - a.lo[0] + 1, ny = a.hi[1] - a.lo[1] + 1;
+  const int i = a.lo[0] + int(c % nx), j = a.lo[1] + int((c / nx) % ny), k = a.lo[2] + int(c / (int64_t(nx) * ny));
+  v.rY = a.rY.p + lane_a4_off(a.rY, i, j, k); v.sY = a.rY.nstride;
+  v.rYsrc = a.rYsrc.p + lane_a4_off(a.rYsrc, i, j, k); v.sS = a.rYsrc.nstride;
+  v.T = a.T.p + lane_a4_off(a.T, i, j, k);
+  v.rE = a.rE.p + lane_a4_off(a.rE, i, j, k);
+  v.rEsrc = a.rEsrc.p + lane_a4_off(a.rEsrc, i, j, k);
+  v.FC = a.FC.p + lane_a4_off(a.FC, i, j, k);
+  v.IR = a.IR.p ? a.IR.p + lane_a4_off(a.IR, i, j, k) : nullptr; v.sI = a.IR.nstride;
+  if (a.mask.p)
+    return a.mask.p[int64_t(i - a.mask.lo[0]) + int64_t(j - a.mask.lo[1]) * a.mask.jstride +
+                    int64_t(k - a.mask.lo[2]) * a.mask.kstride];
+  return 1;
+}
+
+template <class M, class I, class LAY, int EINT>
+__global__ void __launch_bounds__(kLaneThreads, 2)
+    lane_react_kernel(const ReactOpts ro, const BoxArgs a, unsigned long long* __restrict__ counter,
+                      unsigned long long* __restrict__ gstats, int* __restrict__ status, double* __restrict__ ws, int theta)
+{
+  constexpr int NS = M::NS;
+  constexpr bool BDF = I::kBdf;
+  constexpr int TOTAL = BDF ? LAY::TOTAL_BDF : LAY::TOTAL_RK;
+  __shared__ double s_typ[kMaxN];
+  for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) s_typ[i] = ro.typ_vals[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const Ws w{ws + size_t(gwarp) * TOTAL * 32 + lane};
+  LaneOpts o;
+  o.rtol = ro.rtol; o.atol = ro.atol; o.qmax = ro.qmax; o.maxcor = ro.maxcor; o.use_typ = ro.use_typ;
+  o.mxstep = 10000; o.maxnef = 100; o.msbj = 100;
+  o.rk64_guess = ro.rk64_guess; o.rk64_min = ro.rk64_min; o.rk64_max = ro.rk64_max;
+  o.typ_vals = s_typ;
+  CellCfg g;
+  g.time = a.time; g.dt = a.dt; g.dt_inv = a.dt_inv; g.flat = a.flat; g.mks = a.mks;
+  g.clean = (BDF && ro.clean_init_massfrac && !a.flat) ? 1 : 0;
+
+  I it;
+  it.phase = PH_IDLE;
+  int64_t mycell = -1;
+  bool exhausted = false;
+  int wait_acc = 0;
+  const int64_t ncells = a.ncells;
+
+#pragma unroll 1
+  for (;;) {
+    // ---- every idle lane takes the next cell of the queue (one atomic per warp and round) ----
+    const bool want = (it.phase == PH_IDLE) && !exhausted;
+    const unsigned wm = __ballot_sync(0xffffffffu, want);
+    if (wm) {
+      const int leader = __ffs(wm) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(wm));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (want) {
+        const int64_t c = int64_t(base) + __popc(wm & ((1u << lane) - 1u));
+        if (c >= ncells) {
+          exhausted = true;
+        } else {
+          CellView v;
+          const int mk = lane_view<NS>(a, c, v);
+          if (BDF && mk == -1) {  // ReactorCvode.cpp:1395, :1439-1441 (ReactorRK64 ignores the mask)
+            *v.FC = 0.0;
+            if (status) status[c] = 0;
+            atomicAdd(gstats + 8, 1ull);
+            if (a.mks) {  // the reference still scales a skipped cell to CGS and back (PeleLM.cpp:5737-5772): same roundings
+              for (int k = 0; k < NS; ++k) {
+                double* dst = v.rY + k * v.sY;
+                const double vold = *dst, vnew = __dmul_rn(__dmul_rn(vold, 1.0e-3), 1.0e3);
+                if (v.IR) v.IR[k * v.sI] = __dsub_rn(__dmul_rn(-__dsub_rn(vold, vnew), a.dt_inv), v.rYsrc[k * v.sS]);
+                *dst = vnew;
+              }
+              *v.rE = __dmul_rn(__dmul_rn(*v.rE, 10.0), 0.1);
+            }
+          } else {
+            mycell = c;
+            lane_cell_load<M, I, LAY>(it, w, v, g, o);
+          }
+        }
+      }
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, it.phase != PH_IDLE);
+    if (active == 0) {
+      if (__ballot_sync(0xffffffffu, !exhausted) == 0) break;
+      continue;
+    }
+    // ---- (A) + (B) ----
+    lane_round_rhs<M, EINT, I, LAY>(it, w);
+
+    if constexpr (BDF) {
+      // ---- (C) linear-solver setups, when enough lanes wait (or nothing else can run) ----
+      const unsigned waitm = __ballot_sync(0xffffffffu, it.phase == PH_WAIT_SETUP);
+      if (waitm) {
+        const int nwait = __popc(waitm);
+        wait_acc += nwait;
+        const unsigned busy = __ballot_sync(0xffffffffu, it.phase != PH_IDLE && it.phase != PH_WAIT_SETUP);
+        if (wait_acc >= theta || busy == 0) {
+          wait_acc = 0;
+          if (it.phase == PH_WAIT_SETUP) it.setup(w);
+        }
+      }
+      // ---- (D) Newton correction and the step logic behind it, (E) the shared tail ----
+      if (it.phase == PH_SOLVE) it.solve(w);
+      it.tail(w);
+    }
+
+    // ---- cells that finished: final species, then (next round) the temperature; or the store ----
+    if (it.phase == PH_OUT || it.phase == PH_DONE) {
+      CellView v;
+      lane_view<NS>(a, mycell, v);
+      if (it.phase == PH_OUT) lane_cell_out<M, I, LAY>(it, w, v, g);
+      if (it.phase == PH_DONE) {
+        LaneStats st;
+        it.stats(st);
+        const int fc = it.fc();
+        lane_cell_store<M, I, LAY>(it, w, v, g);
+        if (status) status[mycell] = st.flag;
+        atomicAdd(gstats + 0, (unsigned long long)st.nst);
+        atomicAdd(gstats + 1, (unsigned long long)st.nfe);
+        if (BDF) {
+          if (st.nje) atomicAdd(gstats + 2, (unsigned long long)st.nje);
+          if (st.nsetups) atomicAdd(gstats + 3, (unsigned long long)st.nsetups);
+          if (st.nni) atomicAdd(gstats + 4, (unsigned long long)st.nni);
+          if (st.ncfn) atomicAdd(gstats + 5, (unsigned long long)st.ncfn);
+          if (st.netf) atomicAdd(gstats + 6, (unsigned long long)st.netf);
+          if (st.flag != 0) atomicAdd(gstats + 7, 1ull);
+        }
+        atomicAdd(gstats + 9, 1ull);
+        atomicMax(gstats + 10, (unsigned long long)fc);
+        atomicMax(gstats + 11, 0xffffffffull - (unsigned long long)fc);
+      }
+    }
+  }
+}
+
+// one fKernelSpec per thread: y [c][n], ydot [c][n] (the layout of plm_eval_rhs)
+struct PtrSrc {
+  const double* s;
+  double e;
+  __device__ __forceinline__ double operator()(int k) const { return s[k]; }
+  __device__ __forceinline__ double energy() const { return e; }
+};
+template <class M, int EINT>
+__global__ void __launch_bounds__(kLaneThreads, 2)
+    lane_rhs_kernel(int ncells, double t, const double* __restrict__ y, const double* __restrict__ rhoe,
+                    const double* __restrict__ rhoesrc, const double* __restrict__ rYsrc, double* __restrict__ ydot)
+{
+  constexpr int N = M::N, NS = M::NS;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
+    double yy[N], f[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) yy[i] = y[size_t(c) * N + i];
+    PtrSrc src{rYsrc + size_t(c) * NS, rhoesrc[c]};
+    lane_rhs<M, EINT>(yy, f, rhoe[c] + rhoesrc[c] * t, src, false);
+#pragma unroll
+    for (int i = 0; i < N; ++i) ydot[size_t(c) * N + i] = f[i];
+  }
+}
+
+template <int N>
+struct JOut {
+  double* p;
+  __device__ __forceinline__ double& operator()(int r, int c) const { return p[c * N + r]; }
+};
+template <class M>
+__global__ void __launch_bounds__(kLaneThreads, 2) lane_jac_kernel(int ncells, const double* __restrict__ y, double* __restrict__ J)
+{
+  constexpr int N = M::N;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
+    double yy[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) yy[i] = y[size_t(c) * N + i];
+    JOut<N> ja{J + size_t(c) * N * N};
+    lane_cjac<M>(yy, ja);
+  }
+}
+
+}  // namespace lanek
+}  // namespace plm
