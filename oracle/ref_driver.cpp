@@ -69,6 +69,11 @@ int ref_setup()
 
 // (Re)create the reactor through the reference's own factory + ParmParse keys
 // (ReactorCvode.cpp:15-22, :722-726; ReactorRK64.cpp:14-20; PeleLM.cpp:701-709).
+// cells per flat (1dArray) react call the next ref_reactor_init sizes the reference's global N_Vector / user data for
+// (ReactorCvode::init(reactor_type, ncells), ReactorCvode.cpp:33-38); 1 = the box API's per-cell problems
+static int g_init_ncells = 1;
+void ref_set_init_ncells(int n) { g_init_ncells = n > 0 ? n : 1; }
+
 int ref_reactor_init(const char* chem_integrator, const char* solve_type, int reactor_type,
                      double rtol, double atol, int max_order, int max_nls_iters,
                      int clean_init_massfrac, int rk64_guess, int rk64_min, int rk64_max)
@@ -94,7 +99,7 @@ int ref_reactor_init(const char* chem_integrator, const char* solve_type, int re
   }
   g_reactor_type = reactor_type;
   g_reactor = reactions::ReactorBase::create(chem_integrator);
-  return g_reactor->init(reactor_type, 1);
+  return g_reactor->init(reactor_type, g_init_ncells);
 }
 
 int ref_set_typ_vals(const double* typ)

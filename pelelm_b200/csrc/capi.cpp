@@ -261,9 +261,9 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
   }
   if (sl.status.ensure(std::max<int64_t>(a.ncells, 1) * sizeof(int)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
   auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
-  if (lane) {  // one thread per cell: two CTAs of 128 threads per SM, every lane pulls its own cells from the queue
-    const int threads = plm::lane_threads();
-    const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(2 * r->num_sms, (a.ncells + threads - 1) / threads)));
+  if (lane) {  // one thread per cell, one persistent CTA per SM: every lane pulls its own cells from the queue
+    const int threads = plm::lane_threads(m, r->integ, r->opts.qmax);
+    const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(r->num_sms, (a.ncells + threads - 1) / threads)));
     if (sl.lanews.ensure(plm::lane_ws_bytes(m, r->integ, r->opts.qmax, blocks)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
     PLM_CUDA(cudaMemsetAsync(ctrl + si, 0, sizeof(unsigned long long), stream));
     PLM_CUDA(cudaEventRecord(sl.ev0, stream));

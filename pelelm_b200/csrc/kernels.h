@@ -56,7 +56,7 @@ cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const do
 cudaError_t launch_reaction_rate(const DevMech& m, const DevMech* dm, const BoxArgs& a, plm_a4d rhoYdot, cudaStream_t stream);
 // ---- lane = cell path (lane_kernels.cu): one thread per cell, straight-line generated mechanism code ----
 bool lane_supported(const DevMech& m, int integ, const ReactOpts& o);
-int lane_threads();
+int lane_threads(const DevMech& m, int integ, int qmax);   // CTA size; one CTA per SM
 size_t lane_ws_bytes(const DevMech& m, int integ, int qmax, int blocks);   // workspace of a launch with `blocks` CTAs
 cudaError_t launch_lane_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a, int integ, int blocks,
                               unsigned long long* counter, unsigned long long* gstats, int* status, double* ws,

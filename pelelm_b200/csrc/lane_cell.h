@@ -32,8 +32,8 @@ PLM_LHD void lane_cell_load(I& it, const Ws& w, const CellView& c, const CellCfg
 {
   constexpr int ns = M::NS;
   if (g.flat) {  // 1dArray API: [rhoY, T] per cell, T taken as given (ReactorCvode.cpp:1463-1763, CPU branch)
-    for (int k = 0; k <= ns; ++k) w.d(LAY::Y + k) = c.rY[k];
-    for (int k = 0; k < ns; ++k) w.d(LAY::SRC + k) = c.rYsrc[k];
+    for (int k = 0; k <= ns; ++k) w.d(I::YV + k) = c.rY[k];
+    for (int k = 0; k < ns; ++k) w.g(LAY::SRC + k) = c.rYsrc[k];
     it.rhoe_init = *c.rE;
     it.rhoesrc = *c.rEsrc;
     it.begin(w, o, g.time, g.dt, true);
@@ -49,18 +49,18 @@ PLM_LHD void lane_cell_load(I& it, const Ws& w, const CellView& c, const CellCfg
       v = lane_mul(v, 1.0e-3);
       sv = lane_mul(sv, 1.0e-3);
     }
-    w.d(LAY::Y + k) = v;
-    w.d(LAY::SRC + k) = sv;
+    w.d(I::YV + k) = v;
+    w.g(LAY::SRC + k) = sv;
     rho_old += v;
   }
   if (g.clean) {
     for (int k = 0; k < ns; ++k) {
-      const double v = w.d(LAY::Y + k);
+      const double v = w.d(I::YV + k);
       const double lo = 0.0 > v ? 0.0 : v;
-      w.d(LAY::Y + k) = lo < rho_old ? lo : rho_old;
+      w.d(I::YV + k) = lo < rho_old ? lo : rho_old;
     }
   }
-  w.d(LAY::Y + ns) = *c.T;
+  w.d(I::YV + ns) = *c.T;
   it.begin(w, o, g.time, g.dt, false);
 }
 
@@ -91,7 +91,7 @@ PLM_LHD void lane_cell_out(I& it, const Ws& w, const CellView& c, const CellCfg&
       if (g.mks) r0 = lane_mul(r0, 1.0e-3);
       const double lo = 0.0 > r0 ? 0.0 : r0;
       const double cl = lo < rho_old ? lo : rho_old;
-      w.d(LAY::Y + k) = r0 + (w.d(LAY::Y + k) - cl) * rho_old / rho_oldclipped;
+      w.d(I::YV + k) = r0 + (w.d(I::YV + k) - cl) * rho_old / rho_oldclipped;
     }
   }
   it.hin_load = lane_add(it.rhoe_init, lane_mul(g.dt, it.rhoesrc));  // ReactorUtils.H:180, unfused as the host evaluates it
@@ -104,12 +104,12 @@ PLM_LHD void lane_cell_store(I& it, const Ws& w, const CellView& c, const CellCf
   constexpr int ns = M::NS;
   const double rE_new = lane_add(it.rhoe_init, lane_mul(g.dt, it.rhoesrc));
   if (g.flat) {
-    for (int k = 0; k <= ns; ++k) c.rY[k] = w.d(LAY::Y + k);
+    for (int k = 0; k <= ns; ++k) c.rY[k] = w.d(I::YV + k);
     *c.rE = rE_new;
   } else {
     for (int k = 0; k < ns; ++k) {
       double* dst = c.rY + k * c.sY;
-      const double v = w.d(LAY::Y + k);
+      const double v = w.d(I::YV + k);
       if (g.mks) {  // CGS -> MKS (PeleLM.cpp:5765-5772), then I_R (PeleLM.cpp:5795-5799) from the old value still in place
         const double vnew = lane_mul(v, 1.0e3);
         if (c.IR) c.IR[k * c.sI] = lane_sub(lane_mul(-lane_sub(*dst, vnew), g.dt_inv), c.rYsrc[k * c.sS]);
@@ -118,7 +118,7 @@ PLM_LHD void lane_cell_store(I& it, const Ws& w, const CellView& c, const CellCf
         *dst = v;
       }
     }
-    *c.T = w.d(LAY::Y + ns);
+    *c.T = w.d(I::YV + ns);
     *c.rE = g.mks ? lane_mul(rE_new, 0.1) : rE_new;
   }
   *c.FC = double(it.fc());

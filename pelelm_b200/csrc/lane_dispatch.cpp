@@ -23,7 +23,10 @@ namespace plm {
                                       double*, int, cudaStream_t);                                                        \
   size_t lane_ws_rk64_##MECH();                                                                                           \
   size_t lane_ws_bdf2_##MECH();                                                                                           \
-  size_t lane_ws_bdf5_##MECH();
+  size_t lane_ws_bdf5_##MECH();                                                                                           \
+  int lane_threads_rk64_##MECH();                                                                                         \
+  int lane_threads_bdf2_##MECH();                                                                                         \
+  int lane_threads_bdf5_##MECH();
 PLM_LANE_DECL(LiDryer)
 PLM_LANE_DECL(drm19)
 #undef PLM_LANE_DECL
@@ -62,7 +65,13 @@ bool lane_supported(const DevMech& m, int integ, const ReactOpts& o)
   return o.ajac == 1 && m.eint == 0;
 }
 
-int lane_threads() { return 128; }
+int lane_threads(const DevMech& m, int integ, int qmax)
+{
+  const int id = mech_id(m);
+  if (integ == kIntegRK64) return id == 0 ? lane_threads_rk64_LiDryer() : lane_threads_rk64_drm19();
+  if (qmax <= 2) return id == 0 ? lane_threads_bdf2_LiDryer() : lane_threads_bdf2_drm19();
+  return id == 0 ? lane_threads_bdf5_LiDryer() : lane_threads_bdf5_drm19();
+}
 
 size_t lane_ws_bytes(const DevMech& m, int integ, int qmax, int blocks)
 {
@@ -71,7 +80,7 @@ size_t lane_ws_bytes(const DevMech& m, int integ, int qmax, int blocks)
   if (integ == kIntegRK64) per_cell = id == 0 ? lane_ws_rk64_LiDryer() : lane_ws_rk64_drm19();
   else if (qmax <= 2) per_cell = id == 0 ? lane_ws_bdf2_LiDryer() : lane_ws_bdf2_drm19();
   else per_cell = id == 0 ? lane_ws_bdf5_LiDryer() : lane_ws_bdf5_drm19();
-  return per_cell * 32 * size_t(blocks) * (lane_threads() / 32) * sizeof(double);
+  return per_cell * 32 * size_t(blocks) * (lane_threads(m, integ, qmax) / 32) * sizeof(double);
 }
 
 cudaError_t launch_lane_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a, int integ, int blocks,

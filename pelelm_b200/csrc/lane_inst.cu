@@ -17,16 +17,25 @@ using namespace lane;
 using namespace lanek;
 using M = PLM_CAT(Mech_, LANE_MECH);
 
+template <class I, class LAY, int EINT>
+static cudaError_t launch_kernel(const ReactOpts& o, const BoxArgs& a, int blocks, unsigned long long* counter,
+                                 unsigned long long* gstats, int* status, double* ws, int theta, cudaStream_t stream)
+{
+  using SH = LaneShape<I, LAY>;
+  auto kern = lane_react_kernel<M, I, LAY, EINT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SH::SMEM);
+  if (e != cudaSuccess) return e;
+  kern<<<blocks, SH::THREADS, SH::SMEM, stream>>>(o, a, counter, gstats, status, ws, theta);
+  return cudaGetLastError();
+}
+
 #if LANE_KIND == 0
 cudaError_t PLM_CAT(lane_launch_rk64_, LANE_MECH)(const ReactOpts& o, const BoxArgs& a, int eint, int blocks,
                                                   unsigned long long* counter, unsigned long long* gstats, int* status,
                                                   double* ws, int theta, cudaStream_t stream)
 {
-  if (eint)
-    lane_react_kernel<M, LaneRK64<M, 1>, LaneLay<M, 2>, 1><<<blocks, kLaneThreads, 0, stream>>>(o, a, counter, gstats, status, ws, theta);
-  else
-    lane_react_kernel<M, LaneRK64<M, 0>, LaneLay<M, 2>, 0><<<blocks, kLaneThreads, 0, stream>>>(o, a, counter, gstats, status, ws, theta);
-  return cudaGetLastError();
+  if (eint) return launch_kernel<LaneRK64<M, 1>, LaneLay<M, 2>, 1>(o, a, blocks, counter, gstats, status, ws, theta, stream);
+  return launch_kernel<LaneRK64<M, 0>, LaneLay<M, 2>, 0>(o, a, blocks, counter, gstats, status, ws, theta, stream);
 }
 cudaError_t PLM_CAT(lane_launch_rhs_, LANE_MECH)(int eint, int ncells, double t, const double* y, const double* rhoe,
                                                  const double* rhoesrc, const double* rYsrc, double* ydot, cudaStream_t stream)
@@ -42,18 +51,19 @@ cudaError_t PLM_CAT(lane_launch_jac_, LANE_MECH)(int ncells, const double* y, do
   lane_jac_kernel<M><<<blocks, kLaneThreads, 0, stream>>>(ncells, y, J);
   return cudaGetLastError();
 }
-size_t PLM_CAT(lane_ws_rk64_, LANE_MECH)() { return LaneLay<M, 2>::TOTAL_RK; }
+size_t PLM_CAT(lane_ws_rk64_, LANE_MECH)() { return LaneLay<M, 2>::BIG_RK; }
+int PLM_CAT(lane_threads_rk64_, LANE_MECH)() { return LaneShape<LaneRK64<M, 0>, LaneLay<M, 2>>::THREADS; }
 #else
 #define PLM_BDF_NAME PLM_CAT(PLM_CAT(PLM_CAT(lane_launch_bdf, LANE_KIND), _), LANE_MECH)
 #define PLM_WS_NAME PLM_CAT(PLM_CAT(PLM_CAT(lane_ws_bdf, LANE_KIND), _), LANE_MECH)
 cudaError_t PLM_BDF_NAME(const ReactOpts& o, const BoxArgs& a, int blocks, unsigned long long* counter,
                          unsigned long long* gstats, int* status, double* ws, int theta, cudaStream_t stream)
 {
-  lane_react_kernel<M, LaneBdf<M, LANE_KIND, 0>, LaneLay<M, LANE_KIND>, 0><<<blocks, kLaneThreads, 0, stream>>>(
-      o, a, counter, gstats, status, ws, theta);
-  return cudaGetLastError();
+  return launch_kernel<LaneBdf<M, LANE_KIND, 0>, LaneLay<M, LANE_KIND>, 0>(o, a, blocks, counter, gstats, status, ws, theta, stream);
 }
-size_t PLM_WS_NAME() { return LaneLay<M, LANE_KIND>::TOTAL_BDF; }
+size_t PLM_WS_NAME() { return LaneLay<M, LANE_KIND>::BIG_BDF; }
+#define PLM_TH_NAME PLM_CAT(PLM_CAT(PLM_CAT(lane_threads_bdf, LANE_KIND), _), LANE_MECH)
+int PLM_TH_NAME() { return LaneShape<LaneBdf<M, LANE_KIND, 0>, LaneLay<M, LANE_KIND>>::THREADS; }
 #endif
 
 }  // namespace plm

@@ -19,8 +19,8 @@
 //             cvLsSetup/LinSys/Solve cvode/cvode_ls.c:1270-1720, denseGETRF/GETRS sundials/sundials_dense.c:135-232,
 //             N_VWrmsNorm nvector/serial/nvector_serial.c:638-660 (serial sums, in index order, as there).
 //
-// Workspace: per-cell vectors and matrices live in global memory, interleaved over the 32 lanes of the warp
-// (element e of lane l at base[e * 32 + l]): every access of the warp is one fully used 256-byte line.
+// Workspace: see struct Ws -- the vectors in shared memory, the matrices in global memory, both interleaved over the 32
+// lanes of the warp.
 #pragma once
 #include "lane_chem.h"
 
@@ -29,10 +29,17 @@ namespace lane {
 
 constexpr int W = PLM_LANE_W;
 
-// the warp's workspace region; d(e) = element e of this lane
+// The warp's workspace; both parts interleave the 32 lanes (element e of lane l at base[e * 32 + l]) and the pointers
+// are already offset by the lane:
+//   d(e)  FAST space -- the vectors every round touches (Nordsieck array, weights, correction, state, right-hand side):
+//         shared memory on the device (conflict-free for any per-lane element index)
+//   g(e)  BIG space  -- LU factors, saved Jacobian, pivots, external source: global memory (one fully used 256-byte line
+//         per access of the warp; the factors of the resident cells are what the L2 is for)
 struct Ws {
-  double* base;  // already offset by the lane
-  PLM_LHD double& d(int e) const { return base[size_t(e) * W]; }
+  double* fast;
+  double* big;
+  PLM_LHD double& d(int e) const { return fast[size_t(e) * W]; }
+  PLM_LHD double& g(int e) const { return big[size_t(e) * W]; }
 };
 
 struct LaneOpts {
@@ -66,26 +73,29 @@ struct WsSrc {
   Ws w;
   int off;
   double e;
-  PLM_LHD double operator()(int k) const { return w.d(off + k); }
+  PLM_LHD double operator()(int k) const { return w.g(off + k); }
   PLM_LHD double energy() const { return e; }
 };
 
 template <class M, int QM>
 struct LaneLay {
   static constexpr int N = M::N, NS = M::NS;
+  // ---- FAST space (doubles per cell) ----
   static constexpr int ZN = 0;                        // Nordsieck array [(QM+1)][N]   (RK64: soln, carry, err)
   static constexpr int EWT = ZN + (QM + 1) * N;
   static constexpr int ACOR = EWT + N;
   static constexpr int Y = ACOR + N;                  // argument of the right-hand side / result of the cell
-  static constexpr int F = Y + N;                     // last right-hand side
-  static constexpr int DEL = F + N;                   // Newton right-hand side / correction
-  static constexpr int ATOL = DEL + N;                // absolute tolerances (typical values x atol) [N]
-  static constexpr int SRC = ATOL + N;                // external species source [NS]
+  static constexpr int F = Y + N;                     // last right-hand side; then the Newton right-hand side / correction,
+  static constexpr int DEL = F;                       // and the active column of the LU factorisation
+  static constexpr int FAST_BDF = F + N;
+  static constexpr int FAST_RK = 3 * N;
+  // ---- BIG space ----
+  static constexpr int SRC = 0;                       // external species source [NS]
   static constexpr int PERM = SRC + NS;               // pivot rows [N] (stored as doubles)
   static constexpr int MAT = PERM + N;                // LU factors of I - gamma J, column-major [N][N]
   static constexpr int SAV = MAT + N * N;             // saved Jacobian
-  static constexpr int TOTAL_BDF = SAV + N * N;
-  static constexpr int TOTAL_RK = SRC + NS;
+  static constexpr int BIG_BDF = SAV + N * N;
+  static constexpr int BIG_RK = SRC + NS;
   // unroll factor of the vector loops: a divisor of N
   static constexpr int VU = (N % 11 == 0) ? 11 : ((N % 5 == 0) ? 5 : ((N % 6 == 0) ? 6 : 2));
 };
@@ -111,7 +121,8 @@ struct LaneRK64 {
 
   PLM_LHD bool rhs_active() const { return phase == PH_LOAD || phase == PH_RHS0 || phase == PH_FINISH; }
   PLM_LHD bool only_T() const { return phase == PH_LOAD || phase == PH_FINISH; }
-  PLM_LHD int rhs_vec() const { return phase == PH_RHS0 ? SOLN : L::Y; }
+  static constexpr int YV = SOLN;  // where the caller puts the loaded state and finds the result
+  PLM_LHD int rhs_vec() const { return SOLN; }
   PLM_LHD double hin_rho() const
   {
     return phase == PH_RHS0 ? rhoe_init + rhoesrc * (current_time - time_init) : hin_load;
@@ -138,9 +149,7 @@ struct LaneRK64 {
   {
 #pragma unroll(L::VU)
     for (int i = 0; i < N; ++i) {
-      const double v = w.d(L::Y + i);
-      w.d(SOLN + i) = v;
-      w.d(CARRY + i) = v;
+      w.d(CARRY + i) = w.d(SOLN + i);
       w.d(ERR + i) = 0.0;
     }
     phase = (current_time < time_out) ? PH_RHS0 : PH_OUT;
@@ -148,12 +157,12 @@ struct LaneRK64 {
   PLM_LHD void post_rhs(const Ws& w, const double (&f)[N], double T)
   {
     if (phase == PH_LOAD) {
-      w.d(L::Y + NS) = T;
+      w.d(SOLN + NS) = T;
       start(w);
       return;
     }
     if (phase == PH_FINISH) {
-      w.d(L::Y + NS) = T;
+      w.d(SOLN + NS) = T;
       phase = PH_DONE;
       return;
     }
@@ -186,11 +195,7 @@ struct LaneRK64 {
       dt_rk = (dt_rk_min > dt_rk * cf) ? dt_rk_min : dt_rk * cf;
     }
     dt_rk = (dt_rk < time_out - current_time) ? dt_rk : time_out - current_time;
-    if (!(current_time < time_out)) {
-#pragma unroll(L::VU)
-      for (int i = 0; i < N; ++i) w.d(L::Y + i) = w.d(SOLN + i);
-      phase = PH_OUT;
-    }
+    if (!(current_time < time_out)) phase = PH_OUT;
   }
   PLM_LHD void stats(LaneStats& s) const
   {
@@ -237,11 +242,14 @@ struct LaneBdf {
   int q, qprime, Lq, qwait, qmax, maxcor, mxstep, maxnef, msbj;
   int nst, nfe, ncfn, netf, nni, nsetups, nje, nstlp, nstlj, nstloc;
   int jcur, convfail, nflag, ncf, nef, mnewt, call_setup, jbad, nls_jcur, first_res, count1, flag;
+  const double* typ;  // typical values (ReactorBase.cpp:105-123) or nullptr
 
   PLM_LHD bool rhs_active() const { return phase >= PH_LOAD && phase <= PH_ERRF || phase == PH_FINISH; }
   PLM_LHD bool only_T() const { return phase == PH_LOAD || phase == PH_FINISH; }
+  static constexpr int YV = L::Y;  // where the caller puts the loaded state and finds the result
   PLM_LHD int rhs_vec() const { return L::Y; }
   PLM_LHD double hin_rho() const { return only_T() ? hin_load : rhoe_init + rhoesrc * t_eval; }
+  PLM_LHD double atol_of(int i) const { return typ ? typ[i] * atol : atol; }
   PLM_LHD bool wants_setup() const { return phase == PH_WAIT_SETUP; }
   PLM_LHD int fc() const { return nfe; }
   PLM_LHD void stats(LaneStats& s) const
@@ -268,7 +276,7 @@ struct LaneBdf {
     bool bad = false;
 #pragma unroll(VU)
     for (int i = 0; i < N; ++i) {
-      const double t = rtol * lane_fabs(zn(w, 0, i)) + w.d(L::ATOL + i);
+      const double t = rtol * lane_fabs(zn(w, 0, i)) + atol_of(i);
       bad = bad || (t <= 0.0);
       w.d(L::EWT + i) = lane_rcp(t);
     }
@@ -279,7 +287,7 @@ struct LaneBdf {
   PLM_LHD void begin(const Ws& w, const LaneOpts& o, double time, double dt, bool flat)
   {
     rtol = o.rtol; atol = o.atol; qmax = o.qmax; maxcor = o.maxcor; mxstep = o.mxstep; maxnef = o.maxnef; msbj = o.msbj;
-    for (int i = 0; i < N; ++i) w.d(L::ATOL + i) = o.use_typ ? o.typ_vals[i] * o.atol : o.atol;
+    typ = o.use_typ ? o.typ_vals : nullptr;
     t0 = time;
     tout = time + dt;
     hin_load = rhoe_init;
@@ -660,7 +668,7 @@ struct LaneBdf {
   struct JAcc {
     Ws w;
     int off;
-    PLM_LHD double& operator()(int r, int c) const { return w.d(off + c * N + r); }
+    PLM_LHD double& operator()(int r, int c) const { return w.g(off + c * N + r); }
   };
   PLM_LHD void setup(const Ws& w)
   {
@@ -679,16 +687,6 @@ struct LaneBdf {
     } else {
       jcur = 0;
     }
-    // A = I - gamma * J
-    const double c = -gamma;
-    for (int col = 0; col < N; ++col) {
-#pragma unroll(VU)
-      for (int r = 0; r < N; ++r) {
-        double a = w.d(L::SAV + col * N + r) * c;
-        if (r == col) a += 1.0;
-        w.d(L::MAT + col * N + r) = a;
-      }
-    }
     const int ier = getrf(w);
     nsetups++;
     gamrat = 1.0;
@@ -704,54 +702,76 @@ struct LaneBdf {
     mnewt = 0;
     phase = PH_SOLVE;
   }
-  // denseGETRF (partial pivoting, first maximum), column-major; pivot rows kept as doubles in PERM
+  // A = I - gamma J (cvLsLinSys) and denseGETRF (partial pivoting, first maximum) in ONE pass over the saved Jacobian,
+  // column by column ("left-looking"): column j is formed in the FAST space, receives the updates of the finished columns
+  // k < j in the order k = 0, 1, ... (the order, operands and roundings of denseGETRF's right-looking sweeps: the factors
+  // are bit-identical), is searched for its pivot, scaled, and stored once.  Global traffic: every factor is written once
+  // and read n/3 times on average; nothing is read back right after it was written.  Pivot rows kept as doubles in PERM.
   PLM_LHD int getrf(const Ws& w)
   {
+    // the accumulated correction is zero whenever a setup runs (first residual of a Newton attempt): its vector is the
+    // scratch column, and is zeroed again afterwards
+    constexpr int COL = L::ACOR;
+    const double c = -gamma;
     int ier = 0;
-    for (int k = 0; k < N; ++k) {
-      const int ck = L::MAT + k * N;
-      int lp = k;
-      double amax = lane_fabs(w.d(ck + k));
-      for (int i = k + 1; i < N; ++i) {
-        const double v = lane_fabs(w.d(ck + i));
+    for (int j = 0; j < N; ++j) {
+      // column j of I - gamma J with the row interchanges of the columns before it
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double a = w.g(L::SAV + j * N + i) * c;
+        if (i == j) a += 1.0;
+        w.d(COL + i) = a;
+      }
+      for (int k = 0; k < j; ++k) {
+        const int pk = int(w.g(L::PERM + k));
+        if (pk != k) {
+          const double t = w.d(COL + k);
+          w.d(COL + k) = w.d(COL + pk);
+          w.d(COL + pk) = t;
+        }
+      }
+      for (int k = 0; k < j; ++k) {
+        const double a_kj = w.d(COL + k);
+        if (a_kj != 0.0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (i > k) w.d(COL + i) -= a_kj * w.g(L::MAT + k * N + i);
+        }
+      }
+      // pivot of column j
+      int lp = j;
+      double amax = lane_fabs(w.d(COL + j));
+      for (int i = j + 1; i < N; ++i) {
+        const double v = lane_fabs(w.d(COL + i));
         if (v > amax) {
           amax = v;
           lp = i;
         }
       }
-      w.d(L::PERM + k) = double(lp);
-      if (w.d(ck + lp) == 0.0) {
-        ier = k + 1;
+      w.g(L::PERM + j) = double(lp);
+      if (w.d(COL + lp) == 0.0) {
+        ier = j + 1;
         break;
       }
-      if (lp != k) {
-        for (int j = 0; j < N; ++j) {
-          const double t = w.d(L::MAT + j * N + lp);
-          w.d(L::MAT + j * N + lp) = w.d(L::MAT + j * N + k);
-          w.d(L::MAT + j * N + k) = t;
+      if (lp != j) {  // swap rows j and lp: in this column, and in the multipliers already stored
+        const double t = w.d(COL + lp);
+        w.d(COL + lp) = w.d(COL + j);
+        w.d(COL + j) = t;
+        for (int k = 0; k < j; ++k) {
+          const double u = w.g(L::MAT + k * N + lp);
+          w.g(L::MAT + k * N + lp) = w.g(L::MAT + k * N + j);
+          w.g(L::MAT + k * N + j) = u;
         }
       }
-      const double mult = 1.0 / w.d(ck + k);
-      double colk[N];
+      const double mult = 1.0 / w.d(COL + j);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        if (i > k) {
-          colk[i] = w.d(ck + i) * mult;
-          w.d(ck + i) = colk[i];
-        } else {
-          colk[i] = 0.0;
-        }
-      }
-      for (int j = k + 1; j < N; ++j) {
-        const int cj = L::MAT + j * N;
-        const double a_kj = w.d(cj + k);
-        if (a_kj != 0.0) {
-#pragma unroll
-          for (int i = 0; i < N; ++i)
-            if (i > k) w.d(cj + i) -= a_kj * colk[i];
-        }
+        const double v = w.d(COL + i);
+        w.g(L::MAT + j * N + i) = (i > j) ? v * mult : v;
       }
     }
+#pragma unroll
+    for (int i = 0; i < N; ++i) w.d(COL + i) = 0.0;
     return ier;
   }
 
@@ -767,12 +787,17 @@ struct LaneBdf {
       res = -gamma * w.d(L::F + i) + res;
       w.d(L::DEL + i) = -1.0 * res;
     }
-    for (int k = 0; k < N; ++k) {
-      const int pk = int(w.d(L::PERM + k));
-      if (pk != k) {
-        const double t = w.d(L::DEL + k);
-        w.d(L::DEL + k) = w.d(L::DEL + pk);
-        w.d(L::DEL + pk) = t;
+    {
+      int pv[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) pv[k] = int(w.g(L::PERM + k));
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        if (pv[k] != k) {
+          const double t = w.d(L::DEL + k);
+          w.d(L::DEL + k) = w.d(L::DEL + pv[k]);
+          w.d(L::DEL + pv[k]) = t;
+        }
       }
     }
     double b[N];
@@ -781,15 +806,15 @@ struct LaneBdf {
 #pragma unroll
     for (int k = 0; k < N - 1; ++k) {
 #pragma unroll
-      for (int i = k + 1; i < N; ++i) b[i] -= w.d(L::MAT + k * N + i) * b[k];
+      for (int i = k + 1; i < N; ++i) b[i] -= w.g(L::MAT + k * N + i) * b[k];
     }
 #pragma unroll
     for (int k = N - 1; k > 0; --k) {
-      b[k] = lane_div(b[k], w.d(L::MAT + k * N + k));
+      b[k] = lane_div(b[k], w.g(L::MAT + k * N + k));
 #pragma unroll
-      for (int i = 0; i < k; ++i) b[i] -= w.d(L::MAT + k * N + i) * b[k];
+      for (int i = 0; i < k; ++i) b[i] -= w.g(L::MAT + k * N + i) * b[k];
     }
-    b[0] = lane_div(b[0], w.d(L::MAT));
+    b[0] = lane_div(b[0], w.g(L::MAT));
     if (gamrat != 1.0) {
       const double s = 2.0 / (1.0 + gamrat);
 #pragma unroll

@@ -24,7 +24,19 @@ using namespace lane;
 
 namespace lanek {
 
-constexpr int kLaneThreads = 128;
+// CTA shape: one CTA per SM with as many warps (<= 8) as the shared-memory vectors of 32 cells per warp allow
+template <class I, class LAY>
+struct LaneShape {
+  static constexpr int FAST = I::kBdf ? LAY::FAST_BDF : LAY::FAST_RK;
+  static constexpr int BIG = I::kBdf ? LAY::BIG_BDF : LAY::BIG_RK;
+  static constexpr int WARP_BYTES = FAST * 32 * 8;
+  static constexpr int FIT = (227 * 1024 - 1024) / WARP_BYTES;
+  static constexpr int WARPS = FIT >= 8 ? 8 : FIT;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int SMEM = WARPS * WARP_BYTES + kMaxN * 8;
+  static_assert(WARPS >= 1, "the per-cell vectors of one warp do not fit in shared memory");
+};
+constexpr int kLaneThreads = 128;   // rhs / jac parity kernels
 
 __device__ __forceinline__ int64_t lane_a4_off(const plm_a4d& a, int i, int j, int k)
 {
@@ -57,19 +69,20 @@ __device__ __forceinline__ int lane_view(const BoxArgs& a, int64_t c, CellView& 
 }
 
 template <class M, class I, class LAY, int EINT>
-__global__ void __launch_bounds__(kLaneThreads, 2)
+__global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
     lane_react_kernel(const ReactOpts ro, const BoxArgs a, unsigned long long* __restrict__ counter,
                       unsigned long long* __restrict__ gstats, int* __restrict__ status, double* __restrict__ ws, int theta)
 {
   constexpr int NS = M::NS;
   constexpr bool BDF = I::kBdf;
-  constexpr int TOTAL = BDF ? LAY::TOTAL_BDF : LAY::TOTAL_RK;
-  __shared__ double s_typ[kMaxN];
+  using SH = LaneShape<I, LAY>;
+  extern __shared__ double lane_smem[];
+  double* s_typ = lane_smem + SH::WARPS * SH::FAST * 32;
   for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) s_typ[i] = ro.typ_vals[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const Ws w{ws + size_t(gwarp) * TOTAL * 32 + lane};
+  const Ws w{lane_smem + size_t(threadIdx.x >> 5) * SH::FAST * 32 + lane, ws + size_t(gwarp) * SH::BIG * 32 + lane};
   LaneOpts o;
   o.rtol = ro.rtol; o.atol = ro.atol; o.qmax = ro.qmax; o.maxcor = ro.maxcor; o.use_typ = ro.use_typ;
   o.mxstep = 10000; o.maxnef = 100; o.msbj = 100;

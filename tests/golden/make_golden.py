@@ -201,6 +201,80 @@ def flamesheet(mech: str):
     print(mech, "flamesheet golden written: T %.0f..%.0f K, FC %d..%d" % (T.min(), T.max(), FC.min(), FC.max()))
 
 
+BIG = {"LiDryer": 1024, "drm19": 1024, "dodecane_lu": 512}
+
+
+def _big_chunk(arg):
+    mech, c0, n = arg
+    from oracle.pyoracle import Ref
+    from pelelm_b200 import synth
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        R = Ref(mech).init(integrator="ReactorCvode", rtol=1e-10, atol=1e-10, max_order=2)
+        R.set_typ_vals(np.full(R.n, -1.0))
+        b = synth.synthetic_batch(mech, n, cell0=c0, seed=synth.DEFAULT_SEED + 301, dt=DT, forcing=True, mask_every=61)
+        res = R.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT)
+    finally:
+        os.dup2(saved, 1)
+    return b, res
+
+
+def big(mech: str):
+    """tests/golden/<mech>_big.npz (VERDICT r01 'what's weak' 2): the headline configuration (ReactorCvode, rtol = atol = 1e-10,
+    order <= 2, dt = 1e-5) on BIG[mech] cells of the bench's own synthetic states, advanced by the unmodified reference, one
+    process per core.  Only the state the parity test needs is stored (inputs are regenerated from the seed)."""
+    import multiprocessing as mp
+    n = BIG[mech]
+    chunk = 16
+    with mp.get_context("spawn").Pool(len(os.sched_getaffinity(0))) as pool:
+        r = pool.map(_big_chunk, [(mech, c, chunk) for c in range(0, n, chunk)], chunksize=1)
+    out = {}
+    for k, i in (("rY", 0), ("T", 1), ("rE", 2), ("FC", 3)):
+        out[k] = np.concatenate([x[1][i] for x in r], axis=-1)
+    out["in_T"] = np.concatenate([x[0]["T"] for x in r])   # to check that the regenerated inputs are the same
+    out["chunk"] = np.array(chunk)
+    np.savez_compressed(os.path.join(HERE, mech + "_big.npz"), **out)
+    print(mech, "big golden written: %d cells, FC %d..%d (mean %.0f)" % (n, out["FC"][out["FC"] > 0].min(), out["FC"].max(), out["FC"].mean()))
+
+
+def flat(mech: str):
+    """tests/golden/<mech>_flat.npz: the 1dArray API react(rY_in, rYsrc_in, rX_in, rX_src_in, dt, time, ncells)
+    (ReactorCvode.cpp:1463-1763, ReactorRK64.cpp:24-165) of the unmodified reference, (a) one call per cell with ncells = 1
+    (per-cell CVODE problem: the semantics the CUDA path implements for every ncells), (b) one call with all cells (the
+    reference then advances ONE coupled system with a shared step size and a norm over all cells: agrees with (a) only to
+    the integration tolerance; kept to document that)."""
+    from oracle.pyoracle import Ref, _p
+    from pelelm_b200 import synth
+    R = Ref(mech)
+    out = {}
+    nc = 24 if mech != "dodecane_lu" else 4
+    for name, integ, ikw, tr in (("cv", "ReactorCvode", dict(rtol=1e-10, atol=1e-10, max_order=2), (900.0, 2600.0)),
+                                 ("rk", "ReactorRK64", dict(atol=1e-10), (900.0, 1150.0))):
+        if name == "rk" and mech == "dodecane_lu":
+            continue
+        b = synth.synthetic_batch(mech, nc, seed=synth.DEFAULT_SEED + 401, dt=DT, forcing=True, t_range=tr)
+        R.init(integrator=integ, **ikw)
+        R.set_typ_vals(np.full(R.n, -1.0))
+        y0 = np.ascontiguousarray(np.concatenate([b["rY"].T, b["T_true"][:, None]], 1))
+        src = np.ascontiguousarray(b["rYsrc"].T)
+        y1, rX1, fc1 = y0.copy(), b["rE"].copy(), np.zeros(nc)
+        for c in range(nc):
+            fc1[c] = R.L.ref_react_flat(1, _p(y1[c]), _p(src[c]), _p(rX1[c:c + 1]), _p(np.ascontiguousarray(b["rEsrc"][c:c + 1])), DT, 0.0)
+        out[name + "/in_y"], out[name + "/in_src"], out[name + "/in_rX"], out[name + "/in_rXsrc"] = y0, src, b["rE"], b["rEsrc"]
+        out[name + "/y"], out[name + "/rX"], out[name + "/FC"] = y1, rX1, fc1
+        yN, rXN = y0.copy(), b["rE"].copy()
+        R.L.ref_set_init_ncells(nc)   # the reference sizes its global vectors at init (ReactorCvode.cpp:33-38)
+        R.init(integrator=integ, **ikw)
+        R.set_typ_vals(np.full(R.n, -1.0))
+        fcN = R.L.ref_react_flat(nc, _p(yN), _p(src), _p(rXN), _p(np.ascontiguousarray(b["rEsrc"])), DT, 0.0)
+        R.L.ref_set_init_ncells(1)
+        out[name + "/y_coupled"], out[name + "/rX_coupled"], out[name + "/FC_coupled"] = yN, rXN, np.array(fcN)
+    np.savez_compressed(os.path.join(HERE, mech + "_flat.npz"), **out)
+    print(mech, "flat golden written:", {k: v.shape for k, v in out.items() if k.endswith("/y")}, "FC", out["cv/FC"][:4], out["cv/FC_coupled"])
+
+
 def knap():
     """KnapSackProcessorMap buckets from the reference's own knapsack() (any libref works)."""
     import ctypes as C
@@ -250,6 +324,11 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "flamesheet":
         for m in ("drm19", "dodecane_lu"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "flamesheet", m])
+    elif len(sys.argv) > 2 and sys.argv[1] in ("big", "flat"):
+        {"big": big, "flat": flat}[sys.argv[1]](sys.argv[2])
+    elif len(sys.argv) > 1 and sys.argv[1] in ("big", "flat"):
+        for m in NCELLS:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), sys.argv[1], m])
     elif len(sys.argv) > 2 and sys.argv[1] == "etype":
         etype(sys.argv[2])
     elif len(sys.argv) > 1 and sys.argv[1] == "etype":

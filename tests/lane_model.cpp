@@ -9,7 +9,9 @@
 #include "lane_chem.h"
 #include "gen/lane_LiDryer.h"
 #include "gen/lane_drm19.h"
+#ifdef LANE_MODEL_DODECANE
 #include "gen/lane_dodecane_lu.h"
+#endif
 #include "lane_cell.h"
 
 using namespace plm::lane;
@@ -54,8 +56,8 @@ template <class M, int EINT, class I, class LAY>
 void react_cells(int is_bdf, const LaneOpts& o, int ncells, double* rY, double* rYsrc, double* T, double* rE, double* rEsrc,
                  double* FC, const int* mask, double dt, double time, int flat, int mks, int clean, double* IR, int* stats8)
 {
-  std::vector<double> wsbuf(size_t(LAY::TOTAL_BDF) + 8, 0.0);
-  Ws w{wsbuf.data()};
+  std::vector<double> fastbuf(size_t(LAY::FAST_BDF) + 8, 0.0), bigbuf(size_t(LAY::BIG_BDF) + 8, 0.0);
+  Ws w{fastbuf.data(), bigbuf.data()};
   CellCfg g{time, dt, 1.0 / dt, flat, mks, clean};
   const int ns = M::NS, n = M::N;
   for (int c = 0; c < ncells; ++c) {
@@ -118,10 +120,15 @@ int react_mech(int integ, int rt, int qmax, const LaneOpts& o, int ncells, doubl
   return 0;
 }
 
+#ifdef LANE_MODEL_DODECANE
+#define DISPATCH_DODECANE(mech, CALL) else if (!std::strcmp(mech, "dodecane_lu")) { using M = Mech_dodecane_lu; CALL; }
+#else
+#define DISPATCH_DODECANE(mech, CALL)
+#endif
 #define DISPATCH(mech, CALL)                                     \
   if (!std::strcmp(mech, "LiDryer")) { using M = Mech_LiDryer; CALL; }   \
   else if (!std::strcmp(mech, "drm19")) { using M = Mech_drm19; CALL; }  \
-  else if (!std::strcmp(mech, "dodecane_lu")) { using M = Mech_dodecane_lu; CALL; } \
+  DISPATCH_DODECANE(mech, CALL)                                  \
   else return -1;
 
 extern "C" {
