@@ -88,6 +88,11 @@ int  plm_advance_chemistry_box(plm_reactor*, const int lo[3], const int hi[3], p
 int  plm_reaction_rate_rhoY(plm_reactor*, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
                             plm_a4i mask, plm_a4d rhoYdot, void* cuda_stream);
 
+/* Cells whose integration has failed so far (status != 0), over the life of the reactor: everything plm_reactor_stats has
+ * collected plus the calls that have finished on their streams since.  Never blocks.  The reference aborts inside CVODE
+ * (cvodeErrHandler, ReactorCvodeUtils.cpp:9-21); a caller that only enqueues work polls this after it has synchronised its
+ * stream (PeleLM.cpp:5774) -- the adaptor does, before every react call, at close() and in print_final_stats. */
+int  plm_reactor_failed_cells(plm_reactor*, long long* nfailed);
 /* Which kernel family the react / eval calls of this reactor run (no reference counterpart; the parity tests use it to hold
  * both families to the same fixtures): 0 = automatic (default: lane = cell kernels -- one thread per cell, straight-line
  * generated mechanism code -- where they cover the request: LiDryer / drm19 with ReactorRK64 or ReactorCvode +

@@ -63,6 +63,9 @@ int orc_cvode_cell(const plm_mech_tables* m, const orc_opts* o, double* y /* n, 
 int orc_rk64_cell(const plm_mech_tables* m, const orc_opts* o, double* y, double rhoe_init, double rhoesrc_ext,
                   const double* rYsrc, double t0, double dt);
 
+int orc_rk64_cell_ex(const plm_mech_tables* m, const orc_opts* o, double* y, double rhoe_init, double rhoesrc_ext,
+                     const double* rYsrc, double t0, double dt, int clamp_inside);
+
 /* react.c -- the operator API (ReactorBase.H:26-55) on FAB-layout arrays */
 typedef struct orc_a4 {
   double* p;

@@ -140,7 +140,7 @@ int orc_react_flat(const plm_mech_tables* m, const orc_opts* o, int use_rk64, do
     memset(&s, 0, sizeof(s));
     double fc;
     if (use_rk64) {
-      fc = (double)orc_rk64_cell(m, o, rY + (long)c * n, rX[c], rXsrc[c], rYsrc + (long)c * ns, time, dt);
+      fc = (double)orc_rk64_cell_ex(m, o, rY + (long)c * n, rX[c], rXsrc[c], rYsrc + (long)c * ns, time, dt, 0);
       s.nst = (long)fc;
     } else {
       orc_cvode_cell(m, o, rY + (long)c * n, rX[c], rXsrc[c], rYsrc + (long)c * ns, time, time + dt, &s);

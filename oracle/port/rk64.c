@@ -15,6 +15,15 @@ static const double err_rk64[6] = {-0.0554699315064507, 0.158481845574980, -0.09
 int orc_rk64_cell(const plm_mech_tables* m, const orc_opts* o, double* soln, double rhoe_init, double rhoesrc_ext,
                   const double* rYsrc, double time_init, double dt_react)
 {
+  return orc_rk64_cell_ex(m, o, soln, rhoe_init, rhoesrc_ext, rYsrc, time_init, dt_react, 1);
+}
+
+/* clamp_inside = 1: react(box) (ReactorRK64.cpp:206-317) limits every new step to the time left (:307, inside the loop);
+ * clamp_inside = 0: the 1dArray react (ReactorRK64.cpp:24-165) applies that limit only AFTER its loop (:141-142), so its last
+ * step runs past time_out -- a quirk of the reference the drop-in reproduces. */
+int orc_rk64_cell_ex(const plm_mech_tables* m, const orc_opts* o, double* soln, double rhoe_init, double rhoesrc_ext,
+                     const double* rYsrc, double time_init, double dt_react, int clamp_inside)
+{
   const int neq = m->ns + 1;
   const double exp1 = 0.25, exp2 = 0.2, betaerr = 1.0, tinyval = 1e-50;
   double carry[ORC_MAXN], err[ORC_MAXN], rhs[ORC_MAXN];
@@ -46,7 +55,7 @@ int orc_rk64_cell(const plm_mech_tables* m, const orc_opts* o, double* soln, dou
       const double cf = betaerr * pow((o->atol / max_err), exp2);
       dt_rk = (dt_rk_min > dt_rk * cf) ? dt_rk_min : dt_rk * cf;
     }
-    dt_rk = (dt_rk < time_out - current_time) ? dt_rk : time_out - current_time;
+    if (clamp_inside) dt_rk = (dt_rk < time_out - current_time) ? dt_rk : time_out - current_time;
   }
   return nsteps;
 }

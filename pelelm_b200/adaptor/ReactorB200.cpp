@@ -50,6 +50,7 @@ void check(int rc, const char* where)
 int ReactorB200Common::b200_init(const char* integrator, int reactor_type, int verbose)
 {
   m_b200_verbose = verbose;
+  m_b200_reactor_type = reactor_type;
   m_is_cvode = std::strcmp(integrator, "ReactorCvode") == 0;
   const char* mech = mechanism_name();
   if (mech == nullptr) amrex::Abort("ReactorB200: libplmchem has no tables for this mechanism");
@@ -68,6 +69,7 @@ int ReactorB200Common::b200_init(const char* integrator, int reactor_type, int v
   pp.query("atol", atol);
   pp.query("max_nls_iters", max_nls_iters);
   pp.query("clean_init_massfrac", clean);
+  m_b200_clean = clean;
   pp.query("rk64_nsubsteps_guess", g);
   pp.query("rk64_nsubsteps_min", mn);
   pp.query("rk64_nsubsteps_max", mx);
@@ -85,8 +87,20 @@ int ReactorB200Common::b200_init(const char* integrator, int reactor_type, int v
   return 0;
 }
 
+// The reference aborts the run when CVODE fails in a cell (cvodeErrHandler, ReactorCvodeUtils.cpp:9-21). The batched kernel
+// records the failure per cell instead; the count of failed cells of every call that has finished is polled here -- before
+// the next call, at close() and in print_final_stats -- so that a GPU build, whose react() only enqueues, does not carry on
+// with the partial state of a failed cell.
+void ReactorB200Common::b200_abort_on_failed_cells()
+{
+  long long nfailed = 0;
+  if (m_handle != nullptr && plm_reactor_failed_cells(m_handle, &nfailed) == PLM_OK && nfailed > 0)
+    amrex::Abort("ReactorB200: integration failed in " + std::to_string(nfailed) + " cells (status per cell: plm_reactor_cell_status)");
+}
+
 void ReactorB200Common::b200_close()
 {
+  b200_abort_on_failed_cells();
   plm_reactor_close(m_handle);
   m_handle = nullptr;
 }
@@ -106,6 +120,7 @@ int ReactorB200Common::b200_react_box(
   void* stream)
 {
   BL_PROFILE("Pele::ReactorB200::react()");
+  b200_abort_on_failed_cells();  // of the calls before this one (a GPU build only enqueues; PeleLM syncs the stream per box)
   check(plm_reactor_set_typ_vals(m_handle, typ_vals.data(), NUM_SPECIES + 1), "plm_reactor_set_typ_vals");
   const int lo[3] = {box.smallEnd(0), box.smallEnd(1), box.smallEnd(2)};
   const int hi[3] = {box.bigEnd(0), box.bigEnd(1), box.bigEnd(2)};
@@ -116,9 +131,13 @@ int ReactorB200Common::b200_react_box(
     &dt_react, &time, stream);
   check(rc, "plm_react_box");
 #ifdef MOD_REACTOR
-  // ReactorCvode.cpp:1444-1449 / ReactorRK64.cpp:319-322 (only ReactEval is built this way)
-  dt_react = time - (time + dt_react);
-  time += dt_react;
+  // only ReactEval is built this way
+  if (m_is_cvode) {  // ReactorCvode.cpp:1444-1449
+    dt_react = time - (time + dt_react);
+    time += dt_react;
+  } else {           // ReactorRK64.cpp:319-321: time = time_out, dt_react untouched
+    time += dt_react;
+  }
 #endif
 #ifndef AMREX_USE_GPU
   // CPU-built caller: results are already back on the host; report like the reference (nfe of the last cell ~ mean)
@@ -142,14 +161,19 @@ int ReactorB200Common::b200_react_flat(
   check(plm_reactor_stats(m_handle, &st), "plm_reactor_stats");
   if (st.nfailed > 0) amrex::Abort("ReactorB200: integration failed in " + std::to_string(st.nfailed) + " cells");
 #ifdef MOD_REACTOR
-  dt_react = time - (time + dt_react);
-  time += dt_react;
+  if (m_is_cvode) {  // ReactorCvode.cpp:1734-1738
+    dt_react = time - (time + dt_react);
+    time += dt_react;
+  } else {           // ReactorRK64.cpp:147-149
+    time += dt_react;
+  }
 #endif
   return st.ncells > 0 ? static_cast<int>((m_is_cvode ? st.nfe : st.nst) / st.ncells) : 0;
 }
 
 void ReactorB200Common::b200_print_stats()
 {
+  b200_abort_on_failed_cells();
   plm_stats st;
   if (plm_reactor_stats(m_handle, &st) != PLM_OK) return;
   amrex::Print() << "-- Final Statistics (libplmchem) --\n"

@@ -19,6 +19,12 @@ SOURCES = ["kernels.cu", "capi.cpp", "dev_tables.cpp", "knapsack.cpp", "lane_dis
            "gen/tables_drm19.c", "gen/tables_dodecane_lu.c"]
 # the lane = cell kernels: one translation unit per (mechanism, kernel family) so the straight-line code compiles in parallel
 LANE_UNITS = [(m, k) for m in ("LiDryer", "drm19") for k in (0, 2, 5)]
+# form of the mechanism code per mechanism: 1 = loops over constant-memory tables (lane_tab.h), 0 = straight-line generated
+# code (lane_chem.h).  drm19's straight-line code is ~180 KB and instruction-fetch bound (profiles/r02b_*); LiDryer's fits.
+# PLM_LANE_TAB="LiDryer=1,drm19=0" overrides (development A/B, with PLM_VARIANT).
+LANE_TAB = {"LiDryer": 0, "drm19": 1}
+for _kv in filter(None, os.environ.get("PLM_LANE_TAB", "").split(",")):
+    LANE_TAB[_kv.split("=")[0]] = int(_kv.split("=")[1])
 
 
 def _newer(src: str, dst: str) -> bool:
@@ -62,15 +68,15 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             jobs.append((cmd, log))
     lane_src = os.path.join(CSRC, "lane_inst.cu")
     for mech, kind in LANE_UNITS:
-        gen = os.path.join(CSRC, "gen", "lane_%s.h" % mech)
+        gen = os.path.join(CSRC, "gen", ("lanetab_%s.h" if LANE_TAB[mech] else "lane_%s.h") % mech)
         obj = os.path.join(objdir, "lane_%s_%d.o" % (mech, kind))
         objs.append(obj)
         t = max([os.path.getmtime(h) for h in lane_hdr] + [os.path.getmtime(gen), os.path.getmtime(lane_src),
                                                            os.path.getmtime(os.path.join(CSRC, "chem_warp.cuh")),
                                                            os.path.getmtime(os.path.join(CSRC, "kernels.h"))])
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < t:
-            cmd = [NVCC] + ARCH + CUFLAGS + ["-I" + CSRC, "-DLANE_MECH=" + mech, "-DLANE_KIND=%d" % kind, "-c", lane_src,
-                                           "-o", obj]
+            cmd = [NVCC] + ARCH + CUFLAGS + ["-I" + CSRC, "-DLANE_MECH=" + mech, "-DLANE_KIND=%d" % kind,
+                                           "-DLANE_TAB=%d" % LANE_TAB[mech], "-c", lane_src, "-o", obj]
             jobs.append((cmd, os.path.join(objdir, "lane_%s_%d.ptxas.log" % (mech, kind))))
     if jobs:
         with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as ex:

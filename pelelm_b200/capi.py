@@ -43,7 +43,7 @@ EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals",
            "plm_advance_chemistry_box", "plm_reaction_rate_rhoY",
            "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
            "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_knapsack_ordered", "plm_least_used_ranks",
-           "plm_measure_fp64_peak", "plm_species_name", "plm_reactor_set_path"]
+           "plm_measure_fp64_peak", "plm_species_name", "plm_reactor_set_path", "plm_reactor_failed_cells"]
 
 _lib = None
 
@@ -82,6 +82,7 @@ def load():
     L.plm_least_used_ranks.argtypes = [C.POINTER(C.c_int64), C.c_int, c_ip]
     L.plm_measure_fp64_peak.argtypes = [c_dp, vp]
     L.plm_reactor_set_path.argtypes = [vp, C.c_int]
+    L.plm_reactor_failed_cells.argtypes = [vp, C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -181,6 +182,12 @@ class Reactor:
         path = {"auto": 0, "warp": 1, "lane": 2}.get(path, path)
         self._chk(self.L.plm_reactor_set_path(self.h, int(path)))
         return self
+
+    def failed_cells(self):
+        """cells whose integration has failed over the life of the reactor (never blocks)"""
+        n = C.c_longlong(0)
+        self._chk(self.L.plm_reactor_failed_cells(self.h, C.byref(n)))
+        return int(n.value)
 
     def set_typ_vals_ode(self, typ):
         typ = np.ascontiguousarray(typ, dtype=np.float64)

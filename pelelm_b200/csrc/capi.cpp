@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -78,6 +79,7 @@ struct CallSlot {
   DevBuf status;   // int per cell
   DevBuf jglobal;  // saved Jacobians when they do not fit in shared memory
   DevBuf lanews;   // lane = cell path: per-cell vectors and matrices of every resident lane
+  DevBuf fcflat;   // 1dArray API: FC of the call (the API returns it through the statistics only)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool used = false;
   int64_t ncells = 0;
@@ -94,8 +96,11 @@ struct plm_reactor {
   DevBuf ctrl;     // [kSlots] work-queue counters, then kStatWords cumulative statistics (unsigned long long)
   CallSlot slot[kSlots];
   int next_slot = 0, last_slot = -1;
-  unsigned long long* host_stats = nullptr;  // pinned
+  unsigned long long* host_stats = nullptr;  // pinned; [kStatWords] = the failed-cell counter as copied after each launch
+  long long failed_total = 0;                // failed cells already collected by plm_reactor_stats
   DevBuf stage[8]; // host-pointer staging: rY rYsrc T rE rEsrc FC mask I_R
+  std::mutex host_mu;  // the staging buffers are one set per reactor: host-pointer calls (CPU-built AMReX, possibly from
+                       // inside an OpenMP tile loop, PeleLM.cpp:5725) are serialised
   DevBuf scratch[6];
   plm_stats last{};
   double pending_ms = 0.0;  // kernel time of completed-but-unreported calls
@@ -150,7 +155,7 @@ int plm_reactor_create(plm_reactor** out, const char* mechanism, const char* int
   }
   if (r->ctrl.ensure((kSlots + kStatWords) * sizeof(unsigned long long)) != 0 ||
       cudaMemset(r->ctrl.p, 0, (kSlots + kStatWords) * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&r->host_stats), kStatWords * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaMallocHost(reinterpret_cast<void**>(&r->host_stats), (kStatWords + 1) * sizeof(unsigned long long)) != cudaSuccess) {
     plm::free_dev_mech(&r->mech);
     r->ctrl.release();
     delete r;
@@ -160,6 +165,7 @@ int plm_reactor_create(plm_reactor** out, const char* mechanism, const char* int
     cudaEventCreate(&sl.ev0);
     cudaEventCreate(&sl.ev1);
   }
+  r->host_stats[kStatWords] = 0;
   *out = r;
   return PLM_OK;
 }
@@ -260,6 +266,10 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
     sl.used = false;
   }
   if (sl.status.ensure(std::max<int64_t>(a.ncells, 1) * sizeof(int)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+  if (a.flat && !a.FC.p) {  // per-call scratch: calls in flight on other streams own other slots
+    if (sl.fcflat.ensure(std::max<int64_t>(a.ncells, 1) * sizeof(double)) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+    a.FC.p = static_cast<double*>(sl.fcflat.p);
+  }
   auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
   if (lane) {  // one thread per cell, one persistent CTA per SM: every lane pulls its own cells from the queue
     const int threads = plm::lane_threads(m, r->integ, r->opts.qmax);
@@ -270,6 +280,7 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
     PLM_CUDA(plm::launch_lane_react(m, r->opts, a, r->integ, blocks, ctrl + si, ctrl + kSlots, static_cast<int*>(sl.status.p),
                                     static_cast<double*>(sl.lanews.p), stream));
     PLM_CUDA(cudaEventRecord(sl.ev1, stream));
+    PLM_CUDA(cudaMemcpyAsync(r->host_stats + kStatWords, ctrl + kSlots + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     sl.used = true;
     sl.ncells = a.ncells;
     r->last_slot = si;
@@ -288,6 +299,7 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
   PLM_CUDA(plm::launch_react(m, r->mech.d, r->opts, a, cfg, r->integ, ctrl + si, ctrl + kSlots,
                              static_cast<int*>(sl.status.p), static_cast<double*>(sl.jglobal.p), stream));
   PLM_CUDA(cudaEventRecord(sl.ev1, stream));
+  PLM_CUDA(cudaMemcpyAsync(r->host_stats + kStatWords, ctrl + kSlots + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
   sl.used = true;
   sl.ncells = a.ncells;
   r->last_slot = si;
@@ -316,6 +328,8 @@ int collect_stats(plm_reactor* r)
   s.min_fc = g[9] ? int64_t(0xffffffffull - g[11]) : 0;  // the kernel keeps max(0xffffffff - fc)
   s.kernel_ms = r->pending_ms;
   r->pending_ms = 0.0;
+  r->failed_total += s.nfailed;
+  r->host_stats[kStatWords] = 0;  // the device counter was just cleared
   return PLM_OK;
 }
 
@@ -329,7 +343,23 @@ int stage_in(DevBuf& buf, const T* host, size_t count, T** dp, cudaStream_t st, 
   return PLM_OK;
 }
 
-size_t a4_count(const plm_a4d& a) { return size_t(a.nstride) * size_t(std::max(a.ncomp, 1)); }
+// doubles of the first `ncomp` components of a FAB view: what the kernel owns of it. PeleLM passes overlapping views of one
+// FAB (rhoY = STemp comps 0.., rhoH = comp N, T = comp N+1; Array4::ncomp counts the REMAINING components of the FAB), so
+// staging or copying back more than the owned components would let one view overwrite another's result.
+size_t a4_count(const plm_a4d& a, int ncomp) { return size_t(a.nstride) * size_t(std::max(ncomp, 1)); }
+
+// 1 device, 0 host, -1 mixed
+int pointer_kind(std::initializer_list<const void*> ps)
+{
+  int kind = -2;
+  for (const void* p : ps) {
+    if (!p) continue;
+    const int k = is_device_ptr(p) ? 1 : 0;
+    if (kind == -2) kind = k;
+    else if (kind != k) return -1;
+  }
+  return kind == -2 ? 0 : kind;
+}
 
 }  // namespace
 
@@ -365,7 +395,9 @@ int react_box_impl(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY,
   a.flat = 0;
   a.dt = *dt_react;
   a.time = *time;
-  const bool dev = is_device_ptr(rY.p);
+  const int kind = pointer_kind({rY.p, rYsrc.p, T.p, rEner.p, rEner_src.p, FC.p, mask.p, IR.p});
+  if (kind < 0) return fail(PLM_ERR_ARG, "the arrays of one call must be all host or all device memory");
+  const bool dev = kind == 1;
   a.rY = rY; a.rYsrc = rYsrc; a.T = T; a.rE = rEner; a.rEsrc = rEner_src; a.FC = FC; a.mask = mask;
   a.mks = mks;
   a.IR = IR;
@@ -375,28 +407,29 @@ int react_box_impl(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY,
     for (int d = 0; d < 3; ++d)
       if (lo[d] < IR.lo[d] || hi[d] > IR.hi[d]) return fail(PLM_ERR_ARG, "box is not contained in I_R bounds");
   }
+  std::unique_lock<std::mutex> host_lock;
   if (!dev) {
+    host_lock = std::unique_lock<std::mutex>(r->host_mu);
     int rc;
-    if (IR.p && (rc = stage_in(r->stage[7], IR.p, a4_count(IR), &a.IR.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[0], rY.p, a4_count(rY), &a.rY.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[1], rYsrc.p, a4_count(rYsrc), &a.rYsrc.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[2], T.p, a4_count(T), &a.T.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[3], rEner.p, a4_count(rEner), &a.rE.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[4], rEner_src.p, a4_count(rEner_src), &a.rEsrc.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[5], FC.p, a4_count(FC), &a.FC.p, st, true))) return rc;
+    if (IR.p && (rc = stage_in(r->stage[7], IR.p, a4_count(IR, ns), &a.IR.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[0], rY.p, a4_count(rY, ns), &a.rY.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[1], rYsrc.p, a4_count(rYsrc, ns), &a.rYsrc.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[2], T.p, a4_count(T, 1), &a.T.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[3], rEner.p, a4_count(rEner, 1), &a.rE.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[4], rEner_src.p, a4_count(rEner_src, 1), &a.rEsrc.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[5], FC.p, a4_count(FC, 1), &a.FC.p, st, true))) return rc;
     if (mask.p) {
-      const size_t cnt = size_t(mask.nstride) * size_t(std::max(mask.ncomp, 1));
-      if ((rc = stage_in(r->stage[6], mask.p, cnt, &a.mask.p, st, true))) return rc;
+      if ((rc = stage_in(r->stage[6], mask.p, size_t(mask.nstride), &a.mask.p, st, true))) return rc;
     }
   }
   int rc = run_react(r, a, st);
   if (rc != PLM_OK) return rc;
   if (!dev) {
-    PLM_CUDA(cudaMemcpyAsync(rY.p, a.rY.p, a4_count(rY) * sizeof(double), cudaMemcpyDeviceToHost, st));
-    PLM_CUDA(cudaMemcpyAsync(T.p, a.T.p, a4_count(T) * sizeof(double), cudaMemcpyDeviceToHost, st));
-    PLM_CUDA(cudaMemcpyAsync(rEner.p, a.rE.p, a4_count(rEner) * sizeof(double), cudaMemcpyDeviceToHost, st));
-    PLM_CUDA(cudaMemcpyAsync(FC.p, a.FC.p, a4_count(FC) * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (IR.p) PLM_CUDA(cudaMemcpyAsync(IR.p, a.IR.p, a4_count(IR) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(rY.p, a.rY.p, a4_count(rY, ns) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(T.p, a.T.p, a4_count(T, 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(rEner.p, a.rE.p, a4_count(rEner, 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(FC.p, a.FC.p, a4_count(FC, 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (IR.p) PLM_CUDA(cudaMemcpyAsync(IR.p, a.IR.p, a4_count(IR, ns) * sizeof(double), cudaMemcpyDeviceToHost, st));
     PLM_CUDA(cudaStreamSynchronize(st));
   }
   return PLM_OK;
@@ -444,21 +477,24 @@ int plm_reaction_rate_rhoY(plm_reactor* r, const int lo[3], const int hi[3], plm
   a.ncells = int64_t(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
   a.rY = rhoY; a.rE = rhoH; a.T = T; a.mask = mask;
   plm_a4d out = rhoYdot;
-  const bool dev = is_device_ptr(rhoY.p);
+  const int kind = pointer_kind({rhoY.p, rhoH.p, T.p, mask.p, rhoYdot.p});
+  if (kind < 0) return fail(PLM_ERR_ARG, "the arrays of one call must be all host or all device memory");
+  const bool dev = kind == 1;
+  std::unique_lock<std::mutex> host_lock;
   if (!dev) {
+    host_lock = std::unique_lock<std::mutex>(r->host_mu);
     int rc;
-    if ((rc = stage_in(r->stage[0], rhoY.p, a4_count(rhoY), &a.rY.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[2], T.p, a4_count(T), &a.T.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[3], rhoH.p, a4_count(rhoH), &a.rE.p, st, true))) return rc;
-    if ((rc = stage_in(r->stage[1], rhoYdot.p, a4_count(rhoYdot), &out.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[0], rhoY.p, a4_count(rhoY, ns), &a.rY.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[2], T.p, a4_count(T, 1), &a.T.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[3], rhoH.p, a4_count(rhoH, 1), &a.rE.p, st, true))) return rc;
+    if ((rc = stage_in(r->stage[1], rhoYdot.p, a4_count(rhoYdot, ns), &out.p, st, true))) return rc;
     if (mask.p) {
-      const size_t cnt = size_t(mask.nstride) * size_t(std::max(mask.ncomp, 1));
-      if ((rc = stage_in(r->stage[6], mask.p, cnt, &a.mask.p, st, true))) return rc;
+      if ((rc = stage_in(r->stage[6], mask.p, size_t(mask.nstride), &a.mask.p, st, true))) return rc;
     }
   }
   PLM_CUDA(plm::launch_reaction_rate(r->mech.h, r->mech.d, a, out, st));
   if (!dev) {
-    PLM_CUDA(cudaMemcpyAsync(rhoYdot.p, out.p, a4_count(rhoYdot) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PLM_CUDA(cudaMemcpyAsync(rhoYdot.p, out.p, a4_count(rhoYdot, ns) * sizeof(double), cudaMemcpyDeviceToHost, st));
     PLM_CUDA(cudaStreamSynchronize(st));
   }
   return PLM_OK;
@@ -479,16 +515,19 @@ int plm_react_flat(plm_reactor* r, double* rY, double* rYsrc, double* rX, double
   a.hi[0] = ncells - 1;
   a.dt = *dt_react;
   a.time = *time;
-  const bool dev = is_device_ptr(rY);
+  const int kind = pointer_kind({rY, rYsrc, rX, rX_src});
+  if (kind < 0) return fail(PLM_ERR_ARG, "the arrays of one call must be all host or all device memory");
+  const bool dev = kind == 1;
   double *dY = rY, *dS = rYsrc, *dX = rX, *dXs = rX_src, *dFC = nullptr;
   int rc;
+  std::unique_lock<std::mutex> host_lock;
   if (!dev) {
+    host_lock = std::unique_lock<std::mutex>(r->host_mu);
     if ((rc = stage_in(r->stage[0], rY, size_t(ncells) * n, &dY, st, true))) return rc;
     if ((rc = stage_in(r->stage[1], rYsrc, size_t(ncells) * ns, &dS, st, true))) return rc;
     if ((rc = stage_in(r->stage[3], rX, size_t(ncells), &dX, st, true))) return rc;
     if ((rc = stage_in(r->stage[4], rX_src, size_t(ncells), &dXs, st, true))) return rc;
   }
-  if ((rc = stage_in(r->stage[5], static_cast<double*>(nullptr), size_t(ncells), &dFC, st, false))) return rc;
   a.rY.p = dY; a.rYsrc.p = dS; a.T.p = dY; a.rE.p = dX; a.rEsrc.p = dXs; a.FC.p = dFC; a.mask.p = nullptr;
   rc = run_react(r, a, st);
   if (rc != PLM_OK) return rc;
@@ -497,6 +536,13 @@ int plm_react_flat(plm_reactor* r, double* rY, double* rYsrc, double* rX, double
     PLM_CUDA(cudaMemcpyAsync(rX, dX, size_t(ncells) * sizeof(double), cudaMemcpyDeviceToHost, st));
     PLM_CUDA(cudaStreamSynchronize(st));
   }
+  return PLM_OK;
+}
+
+int plm_reactor_failed_cells(plm_reactor* r, long long* nfailed)
+{
+  if (!r || !nfailed) return fail(PLM_ERR_ARG, "null argument");
+  *nfailed = r->failed_total + static_cast<long long>(r->host_stats[kStatWords]);
   return PLM_OK;
 }
 
@@ -539,6 +585,7 @@ void plm_reactor_close(plm_reactor* r)
     sl.status.release();
     sl.jglobal.release();
     sl.lanews.release();
+    sl.fcflat.release();
     if (sl.ev0) cudaEventDestroy(sl.ev0);
     if (sl.ev1) cudaEventDestroy(sl.ev1);
   }

@@ -31,7 +31,7 @@ __constant__ double c_err_rk64[6] = {-0.0554699315064507, 0.158481845574980, -0.
 
 template <class L>
 __device__ __forceinline__ int rk64_warp(double* wb, int lane, const ReactOpts& o, double (&soln)[L::NSLOT],
-                                         double time_init, double dt_react, int& nfe)
+                                         double time_init, double dt_react, int& nfe, bool clamp_inside)
 {
   constexpr int NSLOT = L::NSLOT, n = L::N;
   const double exp1 = 0.25, exp2 = 0.2, betaerr = 1.0, tinyval = 1e-50;
@@ -80,7 +80,9 @@ __device__ __forceinline__ int rk64_warp(double* wb, int lane, const ReactOpts& 
       const double cf = betaerr * dexp(exp2 * dlog(o.atol / max_err));
       dt_rk = fmax(dt_rk_min, dt_rk * cf);
     }
-    dt_rk = fmin(dt_rk, time_out - current_time);
+    // react(box) limits every new step to the time left (ReactorRK64.cpp:307); the 1dArray react applies that limit only
+    // after its loop (:141-142), so its last step runs past time_out: reproduced
+    if (clamp_inside) dt_rk = fmin(dt_rk, time_out - current_time);
   }
   return nsteps;
 }
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
         fc = st.nfe;
       } else {
         int nfe = 0;
-        fc = rk64_warp<L>(wb, lane, o, y, a.time, a.dt, nfe);
+        fc = rk64_warp<L>(wb, lane, o, y, a.time, a.dt, nfe, !a.flat);
         st.nst = fc;
         st.nfe = nfe;
       }
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
         const double cf = betaerr * dexp(exp2 * dlog(o.atol / max_err));
         dt_rk = fmax(dt_rk_min, dt_rk * cf);
       }
-      dt_rk = fmin(dt_rk, time_out - current_time);
+      if (!a.flat) dt_rk = fmin(dt_rk, time_out - current_time);
       w[L::SM + S_T] = current_time;
       w[L::SM + S_DT] = dt_rk;
       if (current_time < time_out) continue;

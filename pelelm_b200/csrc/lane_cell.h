@@ -131,12 +131,21 @@ PLM_LHD void lane_round_rhs(I& it, const Ws& w)
 {
   constexpr int N = M::N;
   if (it.rhs_active()) {
-    double y[N], f[N];
+    double f[N];
     const int yo = it.rhs_vec();
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = w.d(yo + i);
     WsSrc src{w, LAY::SRC, it.rhoesrc};
-    const double T = lane_rhs<M, EINT>(y, f, it.hin_rho(), src, it.only_T());
+    double T;
+    if constexpr (M::kTable) {  // loops over the constant-memory tables; vectors stay in fast memory
+      const LV fv{&w.d(I::FV)};
+      T = lt_rhs<M, EINT>(LV{&w.d(yo)}, fv, LV{&w.d(I::SCV)}, LV{&w.d(I::GV)}, it.hin_rho(), src, it.only_T());
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] = fv(i);
+    } else {                    // straight-line generated code on register arrays
+      double y[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = w.d(yo + i);
+      T = lane_rhs<M, EINT>(y, f, it.hin_rho(), src, it.only_T());
+    }
     it.post_rhs(w, f, T);
   }
 }

@@ -10,12 +10,22 @@
 #define PLM_CAT(a, b) PLM_CAT2(a, b)
 #define PLM_STR2(x) #x
 #define PLM_STR(x) PLM_STR2(x)
+// LANE_TAB = 1: the mechanism as loops over constant-memory tables (lane_tab.h, gen/lanetab_<mech>.h);
+// LANE_TAB = 0: as straight-line generated code (lane_chem.h, gen/lane_<mech>.h)
+#if LANE_TAB
+#include PLM_STR(PLM_CAT(gen/lanetab_, LANE_MECH).h)
+#else
 #include PLM_STR(PLM_CAT(gen/lane_, LANE_MECH).h)
+#endif
 
 namespace plm {
 using namespace lane;
 using namespace lanek;
+#if LANE_TAB
+using M = PLM_CAT(Tab_, LANE_MECH);
+#else
 using M = PLM_CAT(Mech_, LANE_MECH);
+#endif
 
 template <class I, class LAY, int EINT>
 static cudaError_t launch_kernel(const ReactOpts& o, const BoxArgs& a, int blocks, unsigned long long* counter,

@@ -23,6 +23,7 @@
 // lanes of the warp.
 #pragma once
 #include "lane_chem.h"
+#include "lane_tab.h"
 
 namespace plm {
 namespace lane {
@@ -86,15 +87,19 @@ struct LaneLay {
   static constexpr int ACOR = EWT + N;
   static constexpr int Y = ACOR + N;                  // argument of the right-hand side / result of the cell
   static constexpr int F = Y + N;                     // last right-hand side; then the Newton right-hand side / correction,
-  static constexpr int DEL = F;                       // and the active column of the LU factorisation
-  static constexpr int FAST_BDF = F + N;
-  static constexpr int FAST_RK = 3 * N;
+  static constexpr int DEL = F;                       // Newton right-hand side / correction (in place)
+  static constexpr int SC = F + N;                    // table-driven kernels: concentrations [NS] and g/RT [NS] of the
+  static constexpr int G = SC + NS;                   // right-hand side / Jacobian being evaluated
+  static constexpr int FAST_BDF = M::kTable ? G + NS : F + N;
+  static constexpr int RK_F = 3 * N, RK_SC = RK_F + N, RK_G = RK_SC + NS;   // RK64: soln, carry, err, (f, sc, g)
+  static constexpr int FAST_RK = M::kTable ? RK_G + NS : 3 * N;
   // ---- BIG space ----
   static constexpr int SRC = 0;                       // external species source [NS]
   static constexpr int PERM = SRC + NS;               // pivot rows [N] (stored as doubles)
   static constexpr int MAT = PERM + N;                // LU factors of I - gamma J, column-major [N][N]
   static constexpr int SAV = MAT + N * N;             // saved Jacobian
-  static constexpr int BIG_BDF = SAV + N * N;
+  static constexpr int JSCR = SAV + N * N;            // table-driven Jacobian: h/RT, wdot, d wdot/dT, cp/R [4][NS]
+  static constexpr int BIG_BDF = JSCR + (M::kTable ? 4 * NS : 0);
   static constexpr int BIG_RK = SRC + NS;
   // unroll factor of the vector loops: a divisor of N
   static constexpr int VU = (N % 11 == 0) ? 11 : ((N % 5 == 0) ? 5 : ((N % 6 == 0) ? 6 : 2));
@@ -115,13 +120,14 @@ struct LaneRK64 {
   static constexpr int SOLN = L::ZN, CARRY = L::ZN + N, ERR = L::ZN + 2 * N;
   static constexpr bool kBdf = false;
   int phase = PH_IDLE;
-  int stage, nsteps, nfe, flag;
+  int stage, nsteps, nfe, flag, clamp;
   double time_init, time_out, current_time, dt_rk, dt_rk_min, dt_rk_max, atol;
   double rhoe_init, rhoesrc, hin_load;
 
   PLM_LHD bool rhs_active() const { return phase == PH_LOAD || phase == PH_RHS0 || phase == PH_FINISH; }
   PLM_LHD bool only_T() const { return phase == PH_LOAD || phase == PH_FINISH; }
   static constexpr int YV = SOLN;  // where the caller puts the loaded state and finds the result
+  static constexpr int FV = L::RK_F, SCV = L::RK_SC, GV = L::RK_G;  // table-driven right-hand side: result and scratch
   PLM_LHD int rhs_vec() const { return SOLN; }
   PLM_LHD double hin_rho() const
   {
@@ -142,6 +148,9 @@ struct LaneRK64 {
     flag = 0;
     stage = 0;
     hin_load = rhoe_init;
+    // react(box) limits every new step to the time left (ReactorRK64.cpp:307, inside the loop); the 1dArray react applies
+    // that limit only after its loop (:141-142), so its last step runs past time_out: reproduced
+    clamp = flat ? 0 : 1;
     if (flat) start(w);
     else phase = PH_LOAD;
   }
@@ -194,7 +203,7 @@ struct LaneRK64 {
       const double cf = lane_powc(atol / max_err, 0.2);
       dt_rk = (dt_rk_min > dt_rk * cf) ? dt_rk_min : dt_rk * cf;
     }
-    dt_rk = (dt_rk < time_out - current_time) ? dt_rk : time_out - current_time;
+    if (clamp) dt_rk = (dt_rk < time_out - current_time) ? dt_rk : time_out - current_time;
     if (!(current_time < time_out)) phase = PH_OUT;
   }
   PLM_LHD void stats(LaneStats& s) const
@@ -247,6 +256,7 @@ struct LaneBdf {
   PLM_LHD bool rhs_active() const { return phase >= PH_LOAD && phase <= PH_ERRF || phase == PH_FINISH; }
   PLM_LHD bool only_T() const { return phase == PH_LOAD || phase == PH_FINISH; }
   static constexpr int YV = L::Y;  // where the caller puts the loaded state and finds the result
+  static constexpr int FV = L::F, SCV = L::SC, GV = L::G;  // table-driven right-hand side: result and scratch
   PLM_LHD int rhs_vec() const { return L::Y; }
   PLM_LHD double hin_rho() const { return only_T() ? hin_load : rhoe_init + rhoesrc * t_eval; }
   PLM_LHD double atol_of(int i) const { return typ ? typ[i] * atol : atol; }
@@ -677,11 +687,16 @@ struct LaneBdf {
                     (convfail == cv::CV_FAIL_OTHER);
     if (jb) {
       jcur = 1;
-      double y[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) y[i] = w.d(L::Y + i);
       JAcc ja{w, L::SAV};
-      lane_cjac<M>(y, ja);
+      if constexpr (M::kTable) {
+        lt_cjac<M>(LV{&w.d(L::Y)}, ja, LV{&w.d(L::SC)}, LV{&w.d(L::G)}, LV{&w.g(L::JSCR)}, LV{&w.g(L::JSCR + NS)},
+                   LV{&w.g(L::JSCR + 2 * NS)}, LV{&w.g(L::JSCR + 3 * NS)});
+      } else {
+        double y[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = w.d(L::Y + i);
+        lane_cjac<M>(y, ja);
+      }
       nje++;
       nstlj = nst;
     } else {

@@ -208,7 +208,12 @@ __global__ void __launch_bounds__(kLaneThreads, 2)
 #pragma unroll
     for (int i = 0; i < N; ++i) yy[i] = y[size_t(c) * N + i];
     PtrSrc src{rYsrc + size_t(c) * NS, rhoesrc[c]};
-    lane_rhs<M, EINT>(yy, f, rhoe[c] + rhoesrc[c] * t, src, false);
+    if constexpr (M::kTable) {  // per-thread local arrays (this kernel is a parity entry point, not the integration kernel)
+      double sc[NS], g[NS];
+      lt_rhs<M, EINT>(LVt<1>{yy}, LVt<1>{f}, LVt<1>{sc}, LVt<1>{g}, rhoe[c] + rhoesrc[c] * t, src, false);
+    } else {
+      lane_rhs<M, EINT>(yy, f, rhoe[c] + rhoesrc[c] * t, src, false);
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) ydot[size_t(c) * N + i] = f[i];
   }
@@ -228,7 +233,12 @@ __global__ void __launch_bounds__(kLaneThreads, 2) lane_jac_kernel(int ncells, c
 #pragma unroll
     for (int i = 0; i < N; ++i) yy[i] = y[size_t(c) * N + i];
     JOut<N> ja{J + size_t(c) * N * N};
-    lane_cjac<M>(yy, ja);
+    if constexpr (M::kTable) {
+      double sc[M::NS], g[M::NS], h[M::NS], wd[M::NS], jT[M::NS], cR[M::NS];
+      lt_cjac<M>(LVt<1>{yy}, ja, LVt<1>{sc}, LVt<1>{g}, LVt<1>{h}, LVt<1>{wd}, LVt<1>{jT}, LVt<1>{cR});
+    } else {
+      lane_cjac<M>(yy, ja);
+    }
   }
 }
 

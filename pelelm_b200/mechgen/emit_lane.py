@@ -506,6 +506,7 @@ def emit_header(mech) -> str:
     out.append("struct Mech_%s {\n" % m)
     out.append("  static constexpr int NS = %d, N = NS + 1, NR = %d;\n" % (ns, nr))
     out.append("  static constexpr const char* name() { return \"%s\"; }\n" % m)
+    out.append("  static constexpr bool kTable = false;  // straight-line code (csrc/lane_chem.h)\n")
     # tables as functions of a constant index: the arrays live at namespace scope (a __constant__ cannot be a member)
     out.append("  PLM_LHD static double mw_of(int k);\n  PLM_LHD static double imw_of(int k);\n")
     out.append("%s" % thermo)
@@ -543,5 +544,126 @@ def main():
     print("lane kernels emitted")
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Table-driven lane = cell kernels: the mechanism as constant-memory tables (gen/lanetab_<mech>.h) for the loop-based
+# evaluation in csrc/lane_tab.h.  Same data and order as the flat tables of emit_tables.py; one row per reaction so that
+# every load of the loop body is a warp-uniform constant load.
+# ---------------------------------------------------------------------------------------------------------------
+def emit_tab_header(mech) -> str:
+    from decimal import Decimal
+    m = mech["name"]
+    ns, nr = mech["n_species"], mech["n_reactions"]
+    R = mech["reactions"]
+    th = mech["thermo"]
+    mw = [float(w) for w in mech["mw"]]
+
+    def arr(ctype, name, vals, per=6, fmt=lambda v: repr(float(v))):
+        vals = list(vals) or [0]
+        body = ",\n".join("    " + ", ".join(fmt(v) for v in vals[i:i + per]) for i in range(0, len(vals), per))
+        return "PLM_LCONST %s %s_%s[%d] = {\n%s};\n" % (ctype, name, m, len(vals), body)
+
+    ii = lambda v: str(int(v))  # noqa: E731
+    # thermo: [species][range][24] = cp[5] h[6] g[7] dcp[4] a0m1 pad
+    TH = []
+    for k in range(ns):
+        for rg in (0, 1):
+            row = list(th["cp"][k][rg]) + list(th["h"][k][rg]) + list(th["g"][k][rg]) + list(th["dcp"][k][rg])
+            row.append(float(Decimal(repr(float(th["cp"][k][rg][0]))) - 1))
+            row.append(0.0)
+            assert len(row) == 24
+            TH += row
+    # reactions: [nr][12] doubles, [nr][4] ints
+    RK, RF = [], []
+    for r in R:
+        tr = r.get("troe", [0, 0, 0, 0])
+        typ = r["type"]
+        t1 = typ == 3 and abs(tr[1]) > 1.0e-100 and (1.0 - tr[0]) != 0
+        t2 = typ == 3 and abs(tr[2]) > 1.0e-100 and tr[0] != 0
+        np4 = typ == 3 and bool(r.get("troe_has_T2"))
+        RK += [r["A"], r["b"], r["Ea_R"], r.get("A0", 0.0), r.get("b0", 0.0), r.get("Ea0_R", 0.0),
+               (1.0 - tr[0]) if typ == 3 else 0.0, tr[0], (1 / tr[1]) if t1 else 0.0, (1 / tr[2]) if t2 else 0.0, tr[3], r["dn"],
+               tr[1], tr[2], 0.0, 0.0]
+        # flags: bit0 term1, bit1 term2, bit2 T2 term, bit3 b and Ea both zero, bit4 Jacobian term1 (|T3| > 1e-100), bit5 term2
+        fl = (1 if t1 else 0) | (2 if t2 else 0) | (4 if np4 else 0) | (8 if (r["b"] == 0.0 and r["Ea_R"] == 0.0) else 0) | \
+            (16 if (typ == 3 and abs(tr[1]) > 1e-100) else 0) | (32 if (typ == 3 and abs(tr[2]) > 1e-100) else 0)
+        RF += [typ, 1 if r["reversible"] else 0, fl, 0]
+
+    def csr(lists):
+        off, idx, val = [0], [], []
+        for lst in lists:
+            for i, v in lst:
+                idx.append(int(i))
+                val.append(float(v))
+            off.append(len(idx))
+        return off, idx, val
+
+    reac = [sorted(r["reactants"]) for r in R]
+    prod = [sorted(r["products"]) for r in R]
+    net = [_net(r) for r in R]
+    eff = [[(i, e - 1.0) for i, e in sorted(r["eff"])] for r in R]     # efficiency - 1
+    # Jacobian columns of a reaction (consP = 1): every species the rate depends on, ascending; the third-body coefficient
+    # (efficiency - 1) where listed, and where the species sits on either side
+    jc = []
+    for r, rr, pp, ee in zip(R, reac, prod, eff):
+        cols = {}
+        if r["type"] != 0:
+            for i, e in ee:
+                cols.setdefault(i, [0, 0.0])
+                cols[i][0] |= 1
+                cols[i][1] = e
+        for i, _ in rr:
+            cols.setdefault(i, [0, 0.0])[0] |= 2
+        if r["reversible"]:
+            for i, _ in pp:
+                cols.setdefault(i, [0, 0.0])[0] |= 4
+        jc.append(sorted((i, f, e) for i, (f, e) in cols.items()))
+    joff, jidx, jfl, jef = [0], [], [], []
+    for lst in jc:
+        for i, f, e in lst:
+            jidx.append(i)
+            jfl.append(f)
+            jef.append(e)
+        joff.append(len(jidx))
+    s = []
+    s.append("// GENERATED by pelelm_b200/mechgen/emit_lane.py (emit_tab_header) from data/%s.json -- do not edit.\n" % m)
+    s.append("// %s as constant-memory tables for the loop-based lane = cell kernels (csrc/lane_tab.h): %d species, %d reactions.\n" % (m, ns, nr))
+    s.append("#pragma once\n#include \"../lane_common.h\"\n\nnamespace plm {\nnamespace lane {\n\n")
+    s.append(arr("double", "LT_MW", mw))
+    s.append(arr("double", "LT_IMW", [1.0 / w for w in mw]))
+    s.append(arr("double", "LT_TMID", th["tmid"]))
+    s.append(arr("double", "LT_TH", TH, per=6))
+    s.append(arr("double", "LT_RK", RK, per=4))
+    s.append(arr("int", "LT_RF", RF, per=16, fmt=ii))
+    for nm, lists in (("R", reac), ("P", prod), ("N", net), ("E", eff)):
+        off, idx, val = csr(lists)
+        s.append(arr("int", "LT_%sOFF" % nm, off, per=24, fmt=ii))
+        s.append(arr("int", "LT_%sIDX" % nm, idx, per=24, fmt=ii))
+        s.append(arr("double", "LT_%sVAL" % nm, val, per=8))
+    s.append(arr("int", "LT_JOFF", joff, per=24, fmt=ii))
+    s.append(arr("int", "LT_JIDX", jidx, per=24, fmt=ii))
+    s.append(arr("int", "LT_JFL", jfl, per=24, fmt=ii))
+    s.append(arr("double", "LT_JEF", jef, per=8))
+    s.append("\nstruct Tab_%s {\n" % m)
+    s.append("  static constexpr int NS = %d, N = NS + 1, NR = %d;\n" % (ns, nr))
+    s.append("  static constexpr const char* name() { return \"%s\"; }\n" % m)
+    s.append("  static constexpr bool kTable = true;  // loops over constant-memory tables (csrc/lane_tab.h)\n")
+    for nm in ("MW", "IMW", "TMID", "TH", "RK", "ROFF", "RIDX", "RVAL", "POFF", "PIDX", "PVAL", "NOFF", "NIDX", "NVAL", "EOFF", "EIDX",
+               "EVAL", "JOFF", "JIDX", "JFL", "JEF", "RF"):
+        typ = "int" if nm in ("RF", "ROFF", "RIDX", "POFF", "PIDX", "NOFF", "NIDX", "EOFF", "EIDX", "JOFF", "JIDX", "JFL") else "double"
+        s.append("  PLM_LHD static %s %s(int i) { return LT_%s_%s[i]; }\n" % (typ, nm.lower(), nm, m))
+    s.append("  PLM_LHD static double mw_of(int k) { return LT_MW_%s[k]; }\n  PLM_LHD static double imw_of(int k) { return LT_IMW_%s[k]; }\n" % (m, m))
+    s.append("};\n\n}  // namespace lane\n}  // namespace plm\n")
+    return "".join(s)
+
+
+def main_tab():
+    outdir = os.path.join(ROOT, "pelelm_b200", "csrc", "gen")
+    for m in ("LiDryer", "drm19", "dodecane_lu"):
+        with open(os.path.join(outdir, "lanetab_%s.h" % m), "w") as f:
+            f.write(emit_tab_header(load(m)))
+    print("lane tables emitted")
+
+
 if __name__ == "__main__":
     main()
+    main_tab()

@@ -56,9 +56,26 @@ def scaled_err(a, ref, rtol, atol):
     return float(np.max(np.abs(a - ref) / (rtol * np.abs(ref) + atol))) if ref.size else 0.0
 
 
+def rel_errors(rY, rYr, atol=1e-10):
+    """Measured relative errors of the species (what BASELINE.md section 3.4 asks to be stated): max |d rhoY_k| / rhoY_k over
+    (a) every species with Y_k > 1e-12 and (b) the species above the integrator's own absolute tolerance (rhoY_k > atol),
+    NaN cells excluded."""
+    ok = ~(np.isnan(rYr).any(0) | np.isnan(rY).any(0))
+    a, r = rY[:, ok], rYr[:, ok]
+    if r.size == 0:
+        return 0.0, 0.0
+    Y = r / r.sum(0, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(a - r) / np.abs(r)
+    s1, s2 = Y > 1e-12, np.abs(r) > atol
+    return (float(rel[s1].max()) if s1.any() else 0.0), (float(rel[s2].max()) if s2.any() else 0.0)
+
+
 def check_state(got, ref, atol, tag="", rtol=1e-6, fc_equal_min=None, fc_rel=None):
-    """got/ref = (rY, T, rE, FC). Parity bar of BASELINE.json north_star: final Y_k and T relative error
-    <= 1e-6 (species below the integrator's own absolute tolerance are compared against 10*atol), rhoH
+    """got/ref = (rY, T, rE, FC). Parity bar of BASELINE.json north_star: final Y_k and T relative error <= 1e-6 at
+    rtol = atol = 1e-10: |d rhoY_k| <= 1e-6 |rhoY_k| + atol (a species below the integrator's own absolute tolerance is
+    compared against that tolerance: two correct integrations agree on it no better -- the reference's CPU build and its
+    own restatement differ by up to 1e-2 relative on Y_k ~ 1e-9 where their step sequences differ in one step), rhoH
     bit-exact (it is in + dt*src in both), NaN cells (RK64 blow-up) identical, skipped cells identical."""
     rY, T, rE, FC = got
     rYr, Tr, rEr, FCr = ref
@@ -66,7 +83,9 @@ def check_state(got, ref, atol, tag="", rtol=1e-6, fc_equal_min=None, fc_rel=Non
     nan_g = np.isnan(rY).any(0) | np.isnan(T)
     assert np.array_equal(nan_r, nan_g), tag + ": NaN cell pattern differs"
     ok = ~nan_r
-    e = scaled_err(rY[:, ok], rYr[:, ok], rtol, 10 * atol)
+    # the stated bar (floor = atol) holds at the tolerances it is stated for; where the integrator itself runs at a looser
+    # rtol (comparison rtol = 100 x integrator rtol > 1e-6) two valid step sequences differ by a few integrator tolerances
+    e = scaled_err(rY[:, ok], rYr[:, ok], rtol, atol if rtol <= 1e-6 else 10 * atol)
     assert e <= 1.0, "%s: rhoY scaled error %g" % (tag, e)
     et = scaled_err(T[ok], Tr[ok], rtol, 0.0)
     assert et <= 1.0, "%s: T relative error %g" % (tag, et * rtol)

@@ -9,6 +9,9 @@
 #include "lane_chem.h"
 #include "gen/lane_LiDryer.h"
 #include "gen/lane_drm19.h"
+#include "gen/lanetab_LiDryer.h"
+#include "gen/lanetab_drm19.h"
+#include "gen/lanetab_dodecane_lu.h"
 #ifdef LANE_MODEL_DODECANE
 #include "gen/lane_dodecane_lu.h"
 #endif
@@ -35,8 +38,14 @@ void rhs1(int rt, double t, const double* y, double* ydot, double rhoe, double r
   double yy[M::N], f[M::N];
   for (int i = 0; i < M::N; ++i) yy[i] = y[i];
   Src s{rys, rhoesrc};
-  if (rt == 1) lane_rhs<M, 1>(yy, f, rhoe + rhoesrc * t, s, false);
-  else lane_rhs<M, 0>(yy, f, rhoe + rhoesrc * t, s, false);
+  if constexpr (M::kTable) {
+    double sc[M::NS], g[M::NS];
+    if (rt == 1) lt_rhs<M, 1>(LV{yy}, LV{f}, LV{sc}, LV{g}, rhoe + rhoesrc * t, s, false);
+    else lt_rhs<M, 0>(LV{yy}, LV{f}, LV{sc}, LV{g}, rhoe + rhoesrc * t, s, false);
+  } else {
+    if (rt == 1) lane_rhs<M, 1>(yy, f, rhoe + rhoesrc * t, s, false);
+    else lane_rhs<M, 0>(yy, f, rhoe + rhoesrc * t, s, false);
+  }
   for (int i = 0; i < M::N; ++i) ydot[i] = f[i];
 }
 template <class M>
@@ -46,7 +55,12 @@ void jac1(const double* y, double* J)
   for (int i = 0; i < M::N; ++i) yy[i] = y[i];
   JDense<M::N> ja{J};
   for (int i = 0; i < M::N * M::N; ++i) J[i] = 0.0;
-  lane_cjac<M>(yy, ja);
+  if constexpr (M::kTable) {
+    double sc[M::NS], g[M::NS], h[M::NS], wd[M::NS], jT[M::NS], cR[M::NS];
+    lt_cjac<M>(LV{yy}, ja, LV{sc}, LV{g}, LV{h}, LV{wd}, LV{jT}, LV{cR});
+  } else {
+    lane_cjac<M>(yy, ja);
+  }
 }
 }  // namespace
 
@@ -128,6 +142,9 @@ int react_mech(int integ, int rt, int qmax, const LaneOpts& o, int ncells, doubl
 #define DISPATCH(mech, CALL)                                     \
   if (!std::strcmp(mech, "LiDryer")) { using M = Mech_LiDryer; CALL; }   \
   else if (!std::strcmp(mech, "drm19")) { using M = Mech_drm19; CALL; }  \
+  else if (!std::strcmp(mech, "LiDryer_tab")) { using M = Tab_LiDryer; CALL; }   \
+  else if (!std::strcmp(mech, "drm19_tab")) { using M = Tab_drm19; CALL; }  \
+  else if (!std::strcmp(mech, "dodecane_lu_tab")) { using M = Tab_dodecane_lu; CALL; }  \
   DISPATCH_DODECANE(mech, CALL)                                  \
   else return -1;
 

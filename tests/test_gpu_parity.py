@@ -7,7 +7,9 @@ identical mask/skip behaviour; rhoH bit-exact; FC identical where the port's is.
 import numpy as np
 import pytest
 
-from conftest import MECHS, golden, golden_plm, golden_e, check_state
+import os
+
+from conftest import MECHS, GOLDEN, golden, golden_plm, golden_e, check_state, rel_errors
 from golden.make_golden import CASES, DT
 
 pytestmark = pytest.mark.gpu
@@ -21,12 +23,19 @@ def capi(plm_lib):
     return c
 
 
-def _gpu_react(capi, mech, integ, ikw, b, typ=None, box=None):
+# kernel families to hold to the fixtures: "auto" = what a caller gets (lane = cell kernels for LiDryer / drm19 where they cover
+# the request, warp-per-cell otherwise), "warp" = the warp-per-cell kernels forced (they stay the path of dodecane_lu, of the
+# difference-quotient Jacobian and of the internal-energy BDF, and must stay right for the small mechanisms too)
+def _paths(mech):
+    return ("auto", "warp") if mech != "dodecane_lu" else ("auto",)
+
+
+def _gpu_react(capi, mech, integ, ikw, b, typ=None, box=None, path="auto"):
     kw = dict(ikw)
     rk = integ == "ReactorRK64"
     R = capi.Reactor(mech, integ).init(rtol=kw.get("rtol", kw["atol"]), atol=kw["atol"], max_order=kw.get("max_order", 2),
                                        clean_init_massfrac=kw.get("clean_init_massfrac", 0),
-                                       solve_type=kw.get("solve_type", "denseAJ_direct"))
+                                       solve_type=kw.get("solve_type", "denseAJ_direct")).set_path(path)
     if typ is not None:
         R.set_typ_vals_ode(typ)
     nc = b["T"].size
@@ -37,16 +46,19 @@ def _gpu_react(capi, mech, integ, ikw, b, typ=None, box=None):
     return (a[0], a[2], a[3], a[5]), st, status
 
 
+@pytest.mark.parametrize("path", ["auto", "warp"])
 @pytest.mark.parametrize("mech", MECHS)
 @pytest.mark.parametrize("case", list(CASES) + ["reval"])
-def test_react_vs_reference_golden(capi, mech, case):
+def test_react_vs_reference_golden(capi, mech, case, path):
     g = golden(mech)
     if case + "/rY" not in g:
         pytest.skip("case not generated for this mechanism")
+    if path not in _paths(mech):
+        pytest.skip("one kernel family for this mechanism")
     integ, ikw, _ = CASES.get(case, ("ReactorCvode", dict(rtol=1e-10, atol=1e-10, max_order=2), None))
     b = {k: g[case + "/in_" + k] for k in ("rY", "rYsrc", "T", "rE", "rEsrc", "mask")}
     typ = g[case + "/typ"] if case + "/typ" in g else None
-    got, st, status = _gpu_react(capi, mech, integ, ikw, b, typ)
+    got, st, status = _gpu_react(capi, mech, integ, ikw, b, typ, path=path)
     atol = ikw["atol"] * (typ[:-1, None] if typ is not None else 1.0)
     ref = (g[case + "/rY"], g[case + "/T"], g[case + "/rE"], g[case + "/FC"])
     small = mech != "dodecane_lu"
@@ -105,27 +117,58 @@ def test_jac_vs_reference(capi, mech):
     R.close()
 
 
-@pytest.mark.parametrize("mech", ["LiDryer", "drm19"])
-def test_flat_api_matches_box_api(capi, mech):
-    """react(rY_in[ncells][N+1], ...) (ReactorBase.H:43-55) takes T from the state vector and returns FC through
-    the stats; same integration as the box API once T is the converged one."""
+@pytest.mark.parametrize("mech", MECHS)
+def test_big_batch_vs_reference(capi, mech):
+    """The headline configuration (ReactorCvode, rtol = atol = 1e-10, order <= 2, dt = 1e-5) on every cell of
+    tests/golden/<mech>_big.npz: 1024 / 1024 / 512 cells of the bench's own synthetic states advanced by the unmodified reference.
+    Prints the measured relative errors."""
     from pelelm_b200 import synth
-    nc = 67  # ragged: not a multiple of the warp grab size
-    b = synth.synthetic_batch(mech, nc, seed=9, forcing=True)
-    ikw = dict(rtol=1e-10, atol=1e-10, max_order=2)
-    b["mask"][:] = 1
-    (rY, T, rE, FC), st, _ = _gpu_react(capi, mech, "ReactorCvode", ikw, b)
-    # a second box pass from the converged T gives the T the flat API must be fed
-    R = capi.Reactor(mech, "ReactorCvode").init(**ikw)
-    y = np.ascontiguousarray(np.concatenate([b["rY"].T, b["T_true"][:, None]], 1))
-    src = np.ascontiguousarray(b["rYsrc"].T)
-    rX, rXs = b["rE"].copy(), b["rEsrc"].copy()
-    st2 = R.react_flat(y, src, rX, rXs, DT)
-    R.close()
-    assert st2["ncells"] == nc
-    assert np.array_equal(rX, rE)
-    e = np.abs(y[:, :-1].T - rY) / (1e-6 * np.abs(rY) + 1e-9)
-    assert e.max() <= 1.0, e.max()
+    g = np.load(os.path.join(GOLDEN, mech + "_big.npz"))
+    n, ch = g["T"].size, int(g["chunk"])
+    parts = [synth.synthetic_batch(mech, ch, cell0=c, seed=synth.DEFAULT_SEED + 301, dt=DT, forcing=True, mask_every=61)
+             for c in range(0, n, ch)]
+    b = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=-1)) for k in parts[0]}
+    assert np.array_equal(b["T"], g["in_T"])
+    ref = (g["rY"], g["T"], g["rE"], g["FC"])
+    small = mech != "dodecane_lu"
+    for path in _paths(mech):
+        got, st, status = _gpu_react(capi, mech, "ReactorCvode", dict(rtol=1e-10, atol=1e-10, max_order=2), b, path=path)
+        check_state(got, ref, 1e-10, tag="%s/big/%s" % (mech, path), fc_equal_min=0.98 if small else 0.5,
+                    fc_rel=0.01 if small else 0.05)
+        assert not status.any()
+        r1, r2 = rel_errors(got[0], ref[0])
+        print("%s [%s kernels], %d cells: max relative error of rhoY_k over Y_k > 1e-12: %.2e; over rhoY_k > atol: %.2e; T: %.2e; "
+              "FC identical on %.1f%% of cells, total FC off by %.2e" %
+              (mech, path, n, r1, r2, np.max(np.abs(got[1] / ref[1] - 1)), 100 * np.mean(got[3] == ref[3]),
+               abs(got[3].sum() / ref[3].sum() - 1)))
+        assert r2 <= (1e-6 if small else 1e-4)
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_flat_api_vs_reference(capi, mech):
+    """react(rY_in[ncells][N+1], rYsrc_in, rX_in, rX_src_in, dt, time, ncells) (ReactorBase.H:43-55) against the reference's own
+    1dArray react called with one cell per call (tests/golden/<mech>_flat.npz); every cell is its own CVODE problem here
+    whatever ncells is (include/plm_chem.h).  Includes ReactorRK64's 1dArray quirk: no step-size clamp inside the loop."""
+    g = np.load(os.path.join(GOLDEN, mech + "_flat.npz"))
+    for name, integ in (("cv", "ReactorCvode"), ("rk", "ReactorRK64")):
+        if name + "/y" not in g:
+            continue
+        for path in _paths(mech):
+            R = capi.Reactor(mech, integ).init(rtol=1e-10, atol=1e-10, max_order=2).set_path(path)
+            y, src = g[name + "/in_y"].copy(), np.ascontiguousarray(g[name + "/in_src"])
+            rX, rXs = g[name + "/in_rX"].copy(), np.ascontiguousarray(g[name + "/in_rXsrc"])
+            st = R.react_flat(y, src, rX, rXs, DT)
+            R.close()
+            ok = ~np.isnan(g[name + "/y"]).any(1)
+            assert st["ncells"] == rX.size
+            assert np.array_equal(ok, ~np.isnan(y).any(1)), (name, path)
+            assert np.array_equal(rX[ok], g[name + "/rX"][ok])
+            if not ok.any():
+                continue
+            e = np.abs(y - g[name + "/y"])[ok] / (1e-6 * np.abs(g[name + "/y"][ok]) + 1e-10)
+            assert e.max() <= 1.0, (name, path, e.max())
+            if mech != "dodecane_lu":  # total work: FC of the cells as the reference counts them
+                assert abs(st["nfe" if name == "cv" else "nst"] / g[name + "/FC"][ok].sum() - 1) < 0.01 or not ok.all()
 
 
 def test_device_pointers_equal_host_pointers(capi):

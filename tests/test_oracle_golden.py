@@ -158,3 +158,58 @@ def test_port_flamesheet_profile_vs_reference(port_lib, mech):
     check_state(out, ref, ikw["atol"] * g["typ"][:-1, None], tag=mech + "/flamesheet", rtol=100 * ikw["rtol"],
                 fc_equal_min=0.9 if small else None, fc_rel=0.05 if small else 0.15)
     assert g["in_T"].min() < 400.0 and g["in_T"].max() > 1500.0 and g["FC"].max() > 5 * g["FC"].min()   # cold gas to burnt gas
+
+
+@pytest.mark.parametrize("mech,n", [("LiDryer", 256), ("drm19", 256), ("dodecane_lu", 128)])
+def test_port_big_batch_vs_reference(port_lib, mech, n):
+    """the headline configuration (ReactorCvode, rtol = atol = 1e-10, order <= 2) on the first n cells of
+    tests/golden/<mech>_big.npz (512-1024 cells of the bench's own synthetic states advanced by the reference)"""
+    from conftest import rel_errors
+    from pelelm_b200 import synth
+    g = np.load(os.path.join(GOLDEN, mech + "_big.npz"))
+    ch = int(g["chunk"])
+    parts = [synth.synthetic_batch(mech, ch, cell0=c, seed=synth.DEFAULT_SEED + 301, dt=DT, forcing=True, mask_every=61)
+             for c in range(0, n, ch)]
+    b = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=-1)) for k in parts[0]}
+    assert np.array_equal(b["T"], g["in_T"][:n])
+    P = port_lib.Port(mech).init(rtol=1e-10, atol=1e-10, max_order=2)
+    out = P.react_soa(b["rY"], b["rYsrc"], b["T"], b["rE"], b["rEsrc"], b["mask"], DT, nthreads=8)
+    ref = (np.ascontiguousarray(g["rY"][:, :n]), g["T"][:n], g["rE"][:n], g["FC"][:n])
+    small = mech != "dodecane_lu"
+    check_state(out, ref, 1e-10, tag=mech + "/big", fc_equal_min=0.98 if small else 0.5, fc_rel=0.01 if small else 0.05)
+    r1, r2 = rel_errors(out[0], ref[0])
+    print("%s: max relative error of rhoY_k over Y_k > 1e-12: %.2e; over rhoY_k > atol: %.2e" % (mech, r1, r2))
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_port_flat_api_vs_reference(port_lib, mech):
+    """1dArray API react(rY_in, rYsrc_in, rX_in, rX_src_in, dt, time, ncells) (ReactorCvode.cpp:1463-1763, ReactorRK64.cpp:24-165):
+    the port's per-cell flat driver against the reference called with one cell per call; the reference's coupled
+    all-cells-in-one-system call (shared step size, norm over all cells) agrees only to the integration tolerance."""
+    import ctypes as C
+    g = np.load(os.path.join(GOLDEN, mech + "_flat.npz"))
+    L = port_lib.Port(mech).L
+    L.orc_react_flat.argtypes = [C.c_void_p, C.POINTER(port_lib.Opts), C.c_int] + [port_lib.c_dp] * 4 + \
+        [C.c_double, C.c_double, C.c_int, port_lib.c_dp, C.POINTER(port_lib.Stats)]
+    for name, integ in (("cv", "ReactorCvode"), ("rk", "ReactorRK64")):
+        if name + "/y" not in g:
+            continue
+        P = port_lib.Port(mech).init(integrator=integ, rtol=1e-10, atol=1e-10, max_order=2)
+        y, src = g[name + "/in_y"].copy(), np.ascontiguousarray(g[name + "/in_src"])
+        rX, rXs = g[name + "/in_rX"].copy(), np.ascontiguousarray(g[name + "/in_rXsrc"])
+        FC = np.zeros(rX.size)
+        st = port_lib.Stats()
+        L.orc_react_flat(P.m, C.byref(P.opts), P.use_rk64, port_lib._p(y), port_lib._p(src), port_lib._p(rX), port_lib._p(rXs),
+                         DT, 0.0, rX.size, port_lib._p(FC), C.byref(st))
+        ok = ~np.isnan(g[name + "/y"]).any(1)
+        assert np.array_equal(ok, ~np.isnan(y).any(1))
+        assert np.array_equal(rX[ok], g[name + "/rX"][ok])
+        if not ok.any():   # the explicit integrator blows up on every stiff state of this mechanism: same NaN cells, done
+            continue
+        e = np.abs(y - g[name + "/y"])[ok] / (1e-6 * np.abs(g[name + "/y"][ok]) + 1e-10)
+        assert e.max() <= 1.0, (name, e.max())
+        if mech != "dodecane_lu":
+            assert np.mean(FC[ok] == g[name + "/FC"][ok]) >= 0.9
+        if name == "cv":  # the coupled call: same answer within the integration error, different work
+            ec = np.abs(g["cv/y_coupled"] - g["cv/y"]) / (1e-4 * np.abs(g["cv/y"]) + 1e-8)
+            assert ec.max() <= 1.0, ec.max()
