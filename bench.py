@@ -8,6 +8,11 @@ the dense analytic Jacobian, rtol = atol = 1e-10, max_order 2, dt = 1e-5 s, stat
 (T 900-2600 K, phi 0.5-2, burnt fraction 0-1 with radicals).  N>1: the same per-GPU work (weak scaling), boxes assigned
 by the reference's cost-weighted knapsack on the previous pass's FC; NCCL carries only the cost vector and the statistics.
 
+The same JSON line carries, under "also", the other configurations BASELINE.json names, measured in the same run with the
+same method on a bounded number of steps: dodecane_lu (configs[3]'s mechanism; 2^18 cells per GPU), LiDryer ReactorRK64
+(configs[1], 2^20 cells per GPU) and the 3-level TripleFlame AMR hierarchy at the survey's size (configs[4]; strong scaling,
+boxes re-dealt by the knapsack and moved between ranks over NCCL every pass).  --no-also skips them.
+
 A "step" = one react() pass over every box of the rank's shard, each step from the same pristine state (restored by a
 device-to-device copy inside the timed region).  value = cells advanced by dt per second, whole job, inputs resident in
 HBM; e2e = the same through the C ABI with HOST (pinned) arrays, host<->device copies inside the timed region.
@@ -56,7 +61,9 @@ def parse():
     ap.add_argument("--workload", default="batch", choices=["batch", "tripleflame"],
                     help="batch: BASELINE.json configs[1-3] (default); tripleflame: configs[4], per-level chemistry of a synthetic "
                          "3-level AMR hierarchy with cost-weighted box distribution (pelelm_b200/amr.py)")
-    ap.add_argument("--amr-n0", default="32,64,32", help="level-0 cells of the tripleflame hierarchy (SURVEY cfg5: 64,128,64)")
+    ap.add_argument("--amr-n0", default="64,128,64", help="level-0 cells of the tripleflame hierarchy (SURVEY cfg5: 64,128,64)")
+    ap.add_argument("--no-also", action="store_true", help="only the headline workload, not the nested ones")
+    ap.add_argument("--also-steps", type=int, default=2, help="timed steps of each nested workload (bounded: the default run must end within minutes)")
     return ap.parse_args()
 
 
@@ -75,8 +82,38 @@ def workload_name(a, ncells_total, nboxes):
 _W = {}
 
 
-def _cpu_init(mech, integ, rtol, atol, max_order, kind):
+def cpu_info():
+    """model name, logical CPUs this process may use, and how many physical cores they are"""
+    cpus = sorted(os.sched_getaffinity(0))
+    model, phys, cur = "unknown", set(), {}
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ":" not in ln:
+                if cur and int(cur.get("processor", -1)) in cpus:
+                    phys.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+                cur = {}
+                continue
+            k, v = [x.strip() for x in ln.split(":", 1)]
+            cur[k] = v
+            if k == "model name":
+                model = v
+        if cur and int(cur.get("processor", -1)) in cpus:
+            phys.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+    except OSError:
+        pass
+    return {"cpu_model": model, "logical_cpus": len(cpus), "physical_cores": len(phys) or len(cpus)}
+
+
+def _cpu_init(mech, integ, rtol, atol, max_order, kind, counter=None, cpus=None):
     from oracle import pyoracle
+    if counter is not None and cpus:  # pin this worker to one logical CPU
+        with counter.get_lock():
+            i = counter.value
+            counter.value += 1
+        try:
+            os.sched_setaffinity(0, {cpus[i % len(cpus)]})
+        except OSError:
+            pass
     if kind == "reference":
         devnull = os.open(os.devnull, os.O_WRONLY)
         saved = os.dup(1)
@@ -106,10 +143,12 @@ class CpuArm:
         self.kind = "reference" if pyoracle.ref_available(a.mech) else "port"
         if self.kind == "port":
             pyoracle.build_port()
-        self.cores = len(os.sched_getaffinity(0))
+        cpus = sorted(os.sched_getaffinity(0))
+        self.cores = len(cpus)
+        self.info = cpu_info()
         ctx = mp.get_context("spawn")
         self.pool = ctx.Pool(self.cores, initializer=_cpu_init,
-                             initargs=(a.mech, a.integrator, a.rtol, a.atol, a.max_order, self.kind))
+                             initargs=(a.mech, a.integrator, a.rtol, a.atol, a.max_order, self.kind, ctx.Value("i", 0), cpus))
         self.a = a
         # calibrate: 32 cells on every core
         r = self.pool.map(_cpu_chunk, [(i * 32, 32) for i in range(self.cores)], chunksize=1)
@@ -164,7 +203,8 @@ def run_reference_arm(a):
         "steps": steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall_tot / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a, cells_total, nboxes), "cpu_sample": sample, "mean_fc": fc_tot / n_tot},
-        "cpu_baseline": {"value": value, "unit": "cells*dt/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "cpu_baseline": dict({"value": value, "unit": "cells*dt/s", "cores": arm.cores, "kind": arm.kind, "sample": sample,
+                              "pinned": "one process per logical CPU (sched_setaffinity)"}, **arm.info),
         "e2e": {"value": value, "unit": "cells*dt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -222,12 +262,10 @@ class ClockSampler:
         return out
 
 
-def run_gpu_arm(a):
+def gpu_context():
     import torch
     import torch.distributed as dist
-    from pelelm_b200 import capi, roofline, synth
-    from pelelm_b200 import dist as pd
-
+    from pelelm_b200 import capi
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -237,8 +275,19 @@ def run_gpu_arm(a):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    N = world
     capi.load()
+    return {"rank": rank, "world": world, "local": local, "dev": dev}
+
+
+def run_batch(a, ctx):
+    """BASELINE.json configs[1-3]: returns the JSON line (rank 0) or None"""
+    import torch
+    import torch.distributed as dist
+    from pelelm_b200 import capi, roofline, synth
+    from pelelm_b200 import dist as pd
+
+    rank, world, local, dev = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"]
+    N = world
     m = synth.mech(a.mech)
     ns = m.ns
     cells_per_gpu = a.cells or default_cells(a.mech)
@@ -305,12 +354,23 @@ def run_gpu_arm(a):
     def step():
         """One advance over the local shard + the cost / statistics reductions of advance_chemistry."""
         ids = sorted(boxes)
-        for i, b in enumerate(ids):
-            bx = boxes[b]
-            s = streams[i % len(streams)]
-            with torch.cuda.stream(s):
+        if not R.path_is_per_box():   # lane = cell kernels: every local box in ONE launch (plm_react_boxes)
+            lst = []
+            for b in ids:
+                bx = boxes[b]
                 bx["S"].copy_(bx["S0"], non_blocking=True)
-                react_box(bx, s)
+                S, F = bx["S"], bx["F"]
+                lst.append({"lo": [0, 0, 0], "hi": [box_cells - 1, 0, 0], "rY": S[:ns], "rYsrc": F[:ns], "T": S[ns + 1], "rEner": S[ns],
+                            "rEner_src": F[ns], "FC": bx["FC"], "mask": bx["mask"]})
+            R.react_boxes(lst, DT, stream=main.cuda_stream, sync=False)
+            launches[0] += 1
+        else:
+            for i, b in enumerate(ids):
+                bx = boxes[b]
+                s = streams[i % len(streams)]
+                with torch.cuda.stream(s):
+                    bx["S"].copy_(bx["S0"], non_blocking=True)
+                    react_box(bx, s)
         st = R.stats()  # waits for every launch
         # per-box cost = sum of FC (PeleLM::getFuncCountDM): one launch of the library's reduction kernel over all local boxes
         costs = capi.box_costs(FCall, FCoff).cpu().numpy()
@@ -406,16 +466,22 @@ def run_gpu_arm(a):
         per_core = arm.sample_cells(a.cpu_seconds)
         n, wall, _ = arm.run(per_core)
         arm.close()
-        cpu = {"value": n / wall, "unit": "cells*dt/s", "cores": arm.cores, "kind": arm.kind,
-               "sample": "first %d cells of the same workload, %d processes, %.1f s" % (n, arm.cores, wall)}
+        cpu = dict({"value": n / wall, "unit": "cells*dt/s", "cores": arm.cores, "kind": arm.kind,
+                    "sample": "first %d cells of the same workload, %d processes, %.1f s" % (n, arm.cores, wall),
+                    "pinned": "one process per logical CPU (sched_setaffinity)"}, **arm.info)
 
+    line = None
     if rank == 0:
-        traffic = None
+        # DRAM bytes per launch: NOT measured by this run (ncu cannot wrap the timed region); it is the per-cell figure of the
+        # committed ncu capture of the same kernel (profiles/ncu_traffic.json names it) x the cells of one launch
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                dram_per_cell = json.load(open(tp)).get(a.mech, {}).get("dram_bytes_per_cell")
+                ent = json.load(open(tp)).get(a.mech if a.integrator == "ReactorCvode" else a.mech + "_rk64", {})
+                dram_per_cell = ent.get("dram_bytes_per_cell")
                 traffic = dram_per_cell * box_cells if dram_per_cell else None  # one launch = one box
+                traffic_src = ent.get("source")
             except Exception:
                 traffic = None
         line = {
@@ -428,40 +494,31 @@ def run_gpu_arm(a):
                        "knapsack_efficiency": eff, "per_cell": per_cell, "nfailed": tot["nfailed"],
                        "state_io_GBs": value / N * roofline.state_bytes_per_cell(a.mech) / 1e9},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "DFMA probe measured live on this device (MEASURED_PEAKS.json has no FP64 entry)",
                          "flops_per_cell": flops / max(tot["ncells"], 1)},
             "clocks": clk, "e2e": e2e, "gpu_launches": n_launch,
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
     R.close()
-    if N > 1:
-        dist.destroy_process_group()
+    del boxes
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_amr_arm(a):
+def run_amr(a, ctx):
     """BASELINE.json configs[4]: one step = one PeleLM::advance_chemistry of every level of the synthetic TripleFlame
     hierarchy (dt_L = dt / 2^L), boxes dealt over the GPUs by the knapsack on the previous pass's FC (state map = round
     robin), box payloads moved to the chemistry owner and back, covered I_R averaged down.  Strong scaling: the hierarchy
-    is the same for every N."""
+    is the same for every N.  Returns the JSON line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from pelelm_b200 import amr, capi, roofline
     from pelelm_b200 import dist as pd
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    rank, world, local, dev = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"]
     N = world
-    capi.load()
     n0 = tuple(int(x) for x in a.amr_n0.split(","))
     R = capi.Reactor(a.mech, a.integrator).init(rtol=a.rtol, atol=a.atol, max_order=a.max_order)
     peak_tf = capi.measure_fp64_peak()
@@ -514,6 +571,7 @@ def run_amr_arm(a):
         dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
         dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
         ms, launches = float(t[0].item()), int(t[1].item())
+    line = None
     if rank == 0:
         ncell = [L.ncells() for L in levels]
         cells_total = sum(ncell)
@@ -539,9 +597,43 @@ def run_amr_arm(a):
                          "flops_per_cell": flops / max(gst["ncells"], 1)},
             "clocks": clk, "e2e": None, "gpu_launches": launches,
         }
-        print(json.dumps(line), flush=True)
     R.close()
-    if N > 1:
+    del levels
+    torch.cuda.empty_cache()
+    return line
+
+
+NESTED_KEYS = ("value", "unit", "steps", "warmup", "ms_per_step", "scaling", "config", "roofline", "e2e", "cpu_baseline", "gpu_launches")
+
+
+def run_gpu_arm(a):
+    import copy
+    ctx = gpu_context()
+    if a.workload == "tripleflame":
+        line = run_amr(a, ctx)
+    else:
+        line = run_batch(a, ctx)
+        headline = (a.mech == "drm19" and a.integrator == "ReactorCvode" and not a.cells)
+        if headline and not a.no_also:
+            also = {}
+            ks = max(1, min(a.steps, a.also_steps))
+            for name, kw in (("dodecane_lu", dict(mech="dodecane_lu", integrator="ReactorCvode")),
+                             ("lidryer_rk64", dict(mech="LiDryer", integrator="ReactorRK64")),
+                             ("tripleflame", dict(workload="tripleflame"))):
+                sub = copy.copy(a)
+                for k, v in kw.items():
+                    setattr(sub, k, v)
+                sub.steps, sub.warmup, sub.e2e_steps = ks, 1, (1 if name != "tripleflame" else 0)
+                sub.cpu_seconds = min(a.cpu_seconds, 8.0)
+                r = run_amr(sub, ctx) if name == "tripleflame" else run_batch(sub, ctx)
+                if r is not None:
+                    also[name] = {k: r[k] for k in NESTED_KEYS if k in r}
+            if line is not None:
+                line["also"] = also
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if ctx["world"] > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 
@@ -549,8 +641,6 @@ def main():
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
-    elif a.workload == "tripleflame":
-        run_amr_arm(a)
     else:
         run_gpu_arm(a)
 

@@ -82,6 +82,18 @@ int  plm_advance_chemistry_box(plm_reactor*, const int lo[3], const int hi[3], p
                                plm_a4d frc_rhoY, plm_a4d frc_rhoH, plm_a4d I_R, plm_a4d FC, plm_a4i mask, double dt,
                                void* cuda_stream);
 
+/* Several boxes in ONE launch (device arrays only): react (mks = 0) or the fused advance_chemistry body (mks != 0, time = 0)
+ * over every box of `boxes` -- the MFIter loop of PeleLM::advance_chemistry (PeleLM.cpp:5725-5780) for all local boxes of
+ * a level at once.  The work queue then runs over the cells of all boxes, so its tail (the last, most expensive cells) is
+ * paid once per level instead of once per box.  With the warp-per-cell kernels this is a loop of per-box launches.
+ * The status array of plm_reactor_cell_status covers the boxes in the order given. */
+typedef struct plm_box {
+  int lo[3], hi[3];
+  plm_a4d rY, rYsrc, T, rEner, rEner_src, FC, I_R;   /* I_R.p == NULL: not wanted (and ignored when mks == 0) */
+  plm_a4i mask;                                       /* mask.p == NULL: every cell is integrated */
+} plm_box;
+int  plm_react_boxes(plm_reactor*, int nboxes, const plm_box* boxes, double dt, double time, int mks, void* cuda_stream);
+
 /* reactionRateRhoY over a box (PeleLM_K.H:57-101, called by PeleLM::compute_instantaneous_reaction_rates,
  * PeleLM.cpp:2010-2070): MKS rhoY (N comps), rhoH, T (guess) -> rhoYdot = W_k * wdot_k in kg/m^3/s (N comps);
  * mask < 0 (EB covered) => 0.  T is not modified. */
@@ -99,6 +111,8 @@ int  plm_reactor_failed_cells(plm_reactor*, long long* nfailed);
  * denseAJ_direct on the enthalpy reactor; warp-per-cell kernels otherwise), 1 = warp-per-cell kernels, 2 = lane = cell
  * kernels (react calls fail with PLM_ERR_ARG when they do not cover the request). */
 int  plm_reactor_set_path(plm_reactor*, int path);
+/* 1 when the react calls of this reactor, as initialised, run the lane = cell kernels, else 0 */
+int  plm_reactor_uses_lane(const plm_reactor*);
 /* waits for every outstanding call of this reactor, then returns and clears the accumulated counters */
 int  plm_reactor_stats(plm_reactor*, plm_stats* out);
 /* status word per cell of the last call, in box order (device or host destination) */

@@ -225,13 +225,19 @@ def advance_chemistry_level(L: Level, dt, advance_box, fine: Level | None = None
     moved = int(np.count_nonzero(chem_owner != L.owner))
     # STemp / FTemp in the chemistry map; I_R and FC are produced there
     work = pd.move_boxes(L.data, ("S", "F", "mask"), L.owner, chem_owner, device=device, group=group) if moved else L.data
+    todo = []
     for i, b in enumerate(sorted(work)):
         bx = work[b]
         if "I_R" not in bx:   # a received box: outputs are allocated at the chemistry owner
             ns = bx["F"].shape[0] - 1
             bx["I_R"] = torch.empty((ns, bx["S"].shape[1]), dtype=torch.float64, device=bx["S"].device)
             bx["FC"] = torch.empty(bx["S"].shape[1], dtype=torch.float64, device=bx["S"].device)
-        advance_box(bx, L.shape(b), dt, i)
+        todo.append((bx, L.shape(b)))
+    if hasattr(advance_box, "all_boxes"):   # one launch over every local box of the level (plm_react_boxes)
+        advance_box.all_boxes(todo, dt)
+    else:
+        for i, (bx, shape) in enumerate(todo):
+            advance_box(bx, shape, dt, i)
     if wait is not None:
         wait()
     if moved:
@@ -256,7 +262,7 @@ def advance_hierarchy(levels, dt, advance_box, **kw):
     return out
 
 
-def gpu_advance(reactor, streams=None):
+def gpu_advance(reactor, streams=None, multi=True):
     """(advance_box, wait) for advance_chemistry_level on the GPU: one fused `plm_advance_chemistry_box` launch per box
     (device arrays, the box as its own FAB), launches spread round robin over `streams`; wait() drains them and returns
     the integrator statistics accumulated since the previous wait()."""
@@ -273,12 +279,29 @@ def gpu_advance(reactor, streams=None):
                                   stream=st.cuda_stream if st is not None else None, sync=False)
         launches[0] += 1
 
+    def all_boxes(todo, dt):
+        """every local box of the level in one call: with the lane = cell kernels one launch whose work queue runs over the
+        cells of all boxes (the queue's tail is paid once per level, not once per box); a loop of launches otherwise"""
+        if not todo:
+            return
+        boxes = []
+        for bx, shape in todo:
+            S, F = bx["S"], bx["F"]
+            boxes.append({"lo": [0, 0, 0], "hi": [shape[0] - 1, shape[1] - 1, shape[2] - 1], "rY": S[:ns], "rEner": S[ns],
+                          "T": S[ns + 1], "rYsrc": F[:ns], "rEner_src": F[ns], "I_R": bx["I_R"], "FC": bx["FC"], "mask": bx["mask"]})
+        reactor.react_boxes(boxes, dt, mks=True, stream=torch.cuda.current_stream().cuda_stream, sync=False)
+        launches[0] += len(boxes) if reactor.path_is_per_box() else 1
+
     def wait():
         out = reactor.stats()   # waits for every outstanding launch of this reactor
+        if out.get("nfailed", 0):   # the reference aborts inside CVODE (cvodeErrHandler); do not carry a failed cell's state on
+            raise RuntimeError("chemistry integration failed in %d cells (status per cell: Reactor.cell_status)" % out["nfailed"])
         if streams:
             for st in streams:
                 torch.cuda.current_stream().wait_stream(st)
         return out
 
     advance_box.launches = launches
+    if multi:
+        advance_box.all_boxes = all_boxes
     return advance_box, wait

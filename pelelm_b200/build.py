@@ -20,9 +20,10 @@ SOURCES = ["kernels.cu", "capi.cpp", "dev_tables.cpp", "knapsack.cpp", "lane_dis
 # the lane = cell kernels: one translation unit per (mechanism, kernel family) so the straight-line code compiles in parallel
 LANE_UNITS = [(m, k) for m in ("LiDryer", "drm19") for k in (0, 2, 5)]
 # form of the mechanism code per mechanism: 1 = loops over constant-memory tables (lane_tab.h), 0 = straight-line generated
-# code (lane_chem.h).  drm19's straight-line code is ~180 KB and instruction-fetch bound (profiles/r02b_*); LiDryer's fits.
+# code (lane_chem.h).  Measured on B200 (profiles/r02c_lane_ab*.json): the loop form executes ~3x the instructions of the
+# straight-line form (index loads, address arithmetic, uniform branches) and is 3x slower for LiDryer, 1.7x slower for drm19.
 # PLM_LANE_TAB="LiDryer=1,drm19=0" overrides (development A/B, with PLM_VARIANT).
-LANE_TAB = {"LiDryer": 0, "drm19": 1}
+LANE_TAB = {"LiDryer": 0, "drm19": 0}
 for _kv in filter(None, os.environ.get("PLM_LANE_TAB", "").split(",")):
     LANE_TAB[_kv.split("=")[0]] = int(_kv.split("=")[1])
 

@@ -29,6 +29,11 @@ class A4I(C.Structure):
                 ("lo", C.c_int * 3), ("hi", C.c_int * 3), ("ncomp", C.c_int)]
 
 
+class Box(C.Structure):
+    _fields_ = [("lo", C.c_int * 3), ("hi", C.c_int * 3), ("rY", A4D), ("rYsrc", A4D), ("T", A4D), ("rEner", A4D),
+                ("rEner_src", A4D), ("FC", A4D), ("I_R", A4D), ("mask", A4I)]
+
+
 class Stats(C.Structure):
     _fields_ = [("ncells", C.c_int64), ("nskipped", C.c_int64), ("nst", C.c_int64), ("nfe", C.c_int64),
                 ("nje", C.c_int64), ("nsetups", C.c_int64), ("nni", C.c_int64), ("ncfn", C.c_int64),
@@ -43,7 +48,7 @@ EXPORTS = ["plm_reactor_create", "plm_reactor_init", "plm_reactor_set_typ_vals",
            "plm_advance_chemistry_box", "plm_reaction_rate_rhoY",
            "plm_reactor_stats", "plm_reactor_cell_status", "plm_reactor_close", "plm_num_species", "plm_last_error",
            "plm_eval_rhs", "plm_eval_jac", "plm_box_costs", "plm_knapsack", "plm_knapsack_ordered", "plm_least_used_ranks",
-           "plm_measure_fp64_peak", "plm_species_name", "plm_reactor_set_path", "plm_reactor_failed_cells"]
+           "plm_measure_fp64_peak", "plm_species_name", "plm_reactor_set_path", "plm_reactor_failed_cells", "plm_react_boxes", "plm_reactor_uses_lane"]
 
 _lib = None
 
@@ -82,6 +87,8 @@ def load():
     L.plm_least_used_ranks.argtypes = [C.POINTER(C.c_int64), C.c_int, c_ip]
     L.plm_measure_fp64_peak.argtypes = [c_dp, vp]
     L.plm_reactor_set_path.argtypes = [vp, C.c_int]
+    L.plm_reactor_uses_lane.argtypes = [vp]
+    L.plm_react_boxes.argtypes = [vp, C.c_int, C.POINTER(Box), C.c_double, C.c_double, C.c_int, vp]
     L.plm_reactor_failed_cells.argtypes = [vp, C.POINTER(C.c_longlong)]
     _lib = L
     return L
@@ -177,6 +184,10 @@ class Reactor:
                                           clean_init_massfrac, solve_type.encode(), *rk64))
         return self
 
+    def path_is_per_box(self):
+        """True when a react_boxes call is a loop of per-box launches (warp-per-cell kernels), False when it is one launch"""
+        return not bool(self.L.plm_reactor_uses_lane(self.h))
+
     def set_path(self, path):
         """kernel family: 0 / "auto", 1 / "warp" (one warp per cell), 2 / "lane" (one thread per cell)"""
         path = {"auto": 0, "warp": 1, "lane": 2}.get(path, path)
@@ -244,6 +255,23 @@ class Reactor:
             self._a4(A4D, T, fab_lo, fab_hi, 1), self._a4(A4D, frc_rhoY, fab_lo, fab_hi, ns),
             self._a4(A4D, frc_rhoH, fab_lo, fab_hi, 1), ir, self._a4(A4D, FC, fab_lo, fab_hi, 1), m, float(dt),
             C.c_void_p(stream or 0)))
+        return self.stats() if sync else None
+
+    def react_boxes(self, boxes, dt, time=0.0, mks=False, stream=None, sync=True):
+        """One launch over several boxes (device arrays): `boxes` = dicts with lo, hi, rY, rYsrc, T, rEner, rEner_src, FC and
+        optionally mask, I_R, fab_lo, fab_hi.  mks=True: the fused advance_chemistry body (MKS arrays, I_R written)."""
+        ns = self.ns
+        arr = (Box * len(boxes))()
+        for e, b in zip(arr, boxes):
+            flo, fhi = list(b.get("fab_lo", b["lo"])), list(b.get("fab_hi", b["hi"]))
+            e.lo[:] = list(b["lo"])
+            e.hi[:] = list(b["hi"])
+            e.rY, e.rYsrc = self._a4(A4D, b["rY"], flo, fhi, ns), self._a4(A4D, b["rYsrc"], flo, fhi, ns)
+            e.T, e.rEner = self._a4(A4D, b["T"], flo, fhi, 1), self._a4(A4D, b["rEner"], flo, fhi, 1)
+            e.rEner_src, e.FC = self._a4(A4D, b["rEner_src"], flo, fhi, 1), self._a4(A4D, b["FC"], flo, fhi, 1)
+            e.I_R = self._a4(A4D, b["I_R"], flo, fhi, ns) if b.get("I_R") is not None else A4D()
+            e.mask = self._a4(A4I, b["mask"], flo, fhi, 1) if b.get("mask") is not None else A4I()
+        self._chk(self.L.plm_react_boxes(self.h, len(boxes), arr, float(dt), float(time), 1 if mks else 0, C.c_void_p(stream or 0)))
         return self.stats() if sync else None
 
     def reaction_rate_rhoY(self, box_lo, box_hi, rhoY, rhoH, T, mask, rhoYdot, fab_lo=None, fab_hi=None, stream=None):

@@ -1,6 +1,7 @@
 // C ABI of libplmchem.so (include/plm_chem.h): argument checking, host/device pointer staging,
 // launch configuration, statistics. No chemistry is computed on the host.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -15,6 +16,13 @@
 #include "kernels.h"
 
 namespace {
+
+// NVTX ranges named like the reference's BL_PROFILE regions (ReactorCvode.cpp:1156, :1407, :1477; PeleLM.cpp:5632), so that a
+// timeline of a run through the adaptor reads like the reference's TinyProfiler output
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg)
@@ -80,6 +88,7 @@ struct CallSlot {
   DevBuf jglobal;  // saved Jacobians when they do not fit in shared memory
   DevBuf lanews;   // lane = cell path: per-cell vectors and matrices of every resident lane
   DevBuf fcflat;   // 1dArray API: FC of the call (the API returns it through the statistics only)
+  DevBuf boxtab;   // plm_react_boxes: the boxes of the call (BoxArgs[nboxes], then the cell offsets int64[nboxes + 1])
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool used = false;
   int64_t ncells = 0;
@@ -114,7 +123,8 @@ namespace {
 bool use_lane(const plm_reactor* r)
 {
   if (r->path == 1) return false;
-  return plm::lane_supported(r->mech.h, r->integ, r->opts);
+  if (r->path == 2) return plm::lane_supported(r->mech.h, r->integ, r->opts);
+  return plm::lane_auto(r->mech.h, r->integ, r->opts);
 }
 }  // namespace
 
@@ -271,6 +281,15 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
     a.FC.p = static_cast<double*>(sl.fcflat.p);
   }
   auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
+  if (lane && a.nboxes > 0) {  // the boxes of a multi-box call: host vectors (a.tab / a.off) -> this slot's device table
+    const size_t tb = size_t(a.nboxes) * sizeof(plm::BoxArgs), ob = size_t(a.nboxes + 1) * sizeof(int64_t);
+    if (sl.boxtab.ensure(tb + ob) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
+    PLM_CUDA(cudaMemcpyAsync(sl.boxtab.p, a.tab, tb, cudaMemcpyHostToDevice, stream));
+    PLM_CUDA(cudaMemcpyAsync(static_cast<char*>(sl.boxtab.p) + tb, a.off, ob, cudaMemcpyHostToDevice, stream));
+    PLM_CUDA(cudaStreamSynchronize(stream));  // the host vectors are the caller's locals (pageable memory: the copies are staged)
+    a.tab = static_cast<const plm::BoxArgs*>(sl.boxtab.p);
+    a.off = reinterpret_cast<const int64_t*>(static_cast<char*>(sl.boxtab.p) + tb);
+  }
   if (lane) {  // one thread per cell, one persistent CTA per SM: every lane pulls its own cells from the queue
     const int threads = plm::lane_threads(m, r->integ, r->opts.qmax);
     const int blocks = int(std::max<int64_t>(1, std::min<int64_t>(r->num_sms, (a.ncells + threads - 1) / threads)));
@@ -373,6 +392,7 @@ int react_box_impl(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY,
                    plm_a4d rEner, plm_a4d rEner_src, plm_a4d FC, plm_a4i mask, const double* dt_react,
                    const double* time, void* cuda_stream, int mks, plm_a4d IR)
 {
+  NvtxRange nvtx(mks ? "PLM::advance_chemistry()" : "Pele::ReactorCvode::react()");
   if (!r || !lo || !hi || !dt_react || !time) return fail(PLM_ERR_ARG, "null argument");
   if (!r->inited) return fail(PLM_ERR_ARG, "plm_reactor_init has not been called");
   if (!rY.p || !rYsrc.p || !T.p || !rEner.p || !rEner_src.p || !FC.p) return fail(PLM_ERR_ARG, "null array");
@@ -445,6 +465,65 @@ int plm_react_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rY, 
   return react_box_impl(r, lo, hi, rY, rYsrc, T, rEner, rEner_src, FC, mask, dt_react, time, cuda_stream, 0, plm_a4d{});
 }
 
+int plm_react_boxes(plm_reactor* r, int nboxes, const plm_box* boxes, double dt, double time, int mks, void* cuda_stream)
+{
+  NvtxRange nvtx(mks ? "PLM::advance_chemistry()" : "Pele::ReactorCvode::react()");
+  if (!r || (nboxes > 0 && !boxes)) return fail(PLM_ERR_ARG, "null argument");
+  if (!r->inited) return fail(PLM_ERR_ARG, "plm_reactor_init has not been called");
+  if (nboxes <= 0) return PLM_OK;
+  const double t0 = mks ? 0.0 : time;  // PeleLM.cpp:5751
+  for (int b = 0; b < nboxes; ++b)
+    if (!is_device_ptr(boxes[b].rY.p)) return fail(PLM_ERR_ARG, "plm_react_boxes takes device arrays");
+  if (!use_lane(r)) {  // warp-per-cell kernels: one launch per box (they overlap on the caller's streams as before)
+    for (int b = 0; b < nboxes; ++b) {
+      const plm_box& x = boxes[b];
+      const int rc = react_box_impl(r, x.lo, x.hi, x.rY, x.rYsrc, x.T, x.rEner, x.rEner_src, x.FC, x.mask, &dt, &t0, cuda_stream,
+                                    mks, mks ? x.I_R : plm_a4d{});
+      if (rc != PLM_OK) return rc;
+    }
+    return PLM_OK;
+  }
+  const int ns = r->tables->ns;
+  std::vector<plm::BoxArgs> tab;
+  std::vector<int64_t> off(1, 0);
+  tab.reserve(nboxes);
+  for (int b = 0; b < nboxes; ++b) {
+    const plm_box& x = boxes[b];
+    if (x.hi[0] < x.lo[0] || x.hi[1] < x.lo[1] || x.hi[2] < x.lo[2]) continue;  // empty box
+    if (!x.rY.p || !x.rYsrc.p || !x.T.p || !x.rEner.p || !x.rEner_src.p || !x.FC.p) return fail(PLM_ERR_ARG, "null array");
+    if (x.rY.ncomp < ns || x.rYsrc.ncomp < ns) return fail(PLM_ERR_ARG, "rY/rYsrc need NUM_SPECIES components");
+    const plm_a4d* arrs[6] = {&x.rY, &x.rYsrc, &x.T, &x.rEner, &x.rEner_src, &x.FC};
+    for (int d = 0; d < 3; ++d) {
+      for (auto* ar : arrs)
+        if (x.lo[d] < ar->lo[d] || x.hi[d] > ar->hi[d]) return fail(PLM_ERR_ARG, "box is not contained in an array's bounds");
+      if (x.mask.p && (x.lo[d] < x.mask.lo[d] || x.hi[d] > x.mask.hi[d])) return fail(PLM_ERR_ARG, "box is not contained in mask bounds");
+      if (mks && x.I_R.p && (x.lo[d] < x.I_R.lo[d] || x.hi[d] > x.I_R.hi[d])) return fail(PLM_ERR_ARG, "box is not contained in I_R bounds");
+    }
+    plm::BoxArgs e{};
+    for (int d = 0; d < 3; ++d) {
+      e.lo[d] = x.lo[d];
+      e.hi[d] = x.hi[d];
+    }
+    e.ncells = int64_t(x.hi[0] - x.lo[0] + 1) * (x.hi[1] - x.lo[1] + 1) * (x.hi[2] - x.lo[2] + 1);
+    e.rY = x.rY; e.rYsrc = x.rYsrc; e.T = x.T; e.rE = x.rEner; e.rEsrc = x.rEner_src; e.FC = x.FC; e.mask = x.mask;
+    e.IR = mks ? x.I_R : plm_a4d{};
+    tab.push_back(e);
+    off.push_back(off.back() + e.ncells);
+  }
+  if (tab.empty()) return PLM_OK;
+  plm::BoxArgs a = tab[0];
+  a.ncells = off.back();
+  a.flat = 0;
+  a.dt = dt;
+  a.time = t0;
+  a.mks = mks;
+  a.dt_inv = 1.0 / dt;
+  a.tab = tab.data();
+  a.off = off.data();
+  a.nboxes = int(tab.size());
+  return run_react(r, a, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int plm_advance_chemistry_box(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
                               plm_a4d frc_rhoY, plm_a4d frc_rhoH, plm_a4d I_R, plm_a4d FC, plm_a4i mask, double dt,
                               void* cuda_stream)
@@ -456,6 +535,7 @@ int plm_advance_chemistry_box(plm_reactor* r, const int lo[3], const int hi[3], 
 int plm_reaction_rate_rhoY(plm_reactor* r, const int lo[3], const int hi[3], plm_a4d rhoY, plm_a4d rhoH, plm_a4d T,
                            plm_a4i mask, plm_a4d rhoYdot, void* cuda_stream)
 {
+  NvtxRange nvtx("PLM::reactionRateRhoY()");
   if (!r || !lo || !hi) return fail(PLM_ERR_ARG, "null argument");
   if (!rhoY.p || !rhoH.p || !T.p || !rhoYdot.p) return fail(PLM_ERR_ARG, "null array");
   if (r->reactor_type != 2) return fail(PLM_ERR_ARG, "reactionRateRhoY works on enthalpy (PeleLM_K.H:84-86): reactor_type must be 2");
@@ -503,6 +583,7 @@ int plm_reaction_rate_rhoY(plm_reactor* r, const int lo[3], const int hi[3], plm
 int plm_react_flat(plm_reactor* r, double* rY, double* rYsrc, double* rX, double* rX_src, double* dt_react,
                    double* time, int ncells, void* cuda_stream)
 {
+  NvtxRange nvtx("Pele::ReactorCvode::react():flat");
   if (!r || !rY || !rYsrc || !rX || !rX_src || !dt_react || !time) return fail(PLM_ERR_ARG, "null argument");
   if (!r->inited) return fail(PLM_ERR_ARG, "plm_reactor_init has not been called");
   if (ncells < 0) return fail(PLM_ERR_ARG, "negative ncells");
@@ -546,6 +627,8 @@ int plm_reactor_failed_cells(plm_reactor* r, long long* nfailed)
   return PLM_OK;
 }
 
+int plm_reactor_uses_lane(const plm_reactor* r) { return (r && r->inited && use_lane(r)) ? 1 : 0; }
+
 int plm_reactor_set_path(plm_reactor* r, int path)
 {
   if (!r) return fail(PLM_ERR_ARG, "null reactor");
@@ -586,6 +669,7 @@ void plm_reactor_close(plm_reactor* r)
     sl.jglobal.release();
     sl.lanews.release();
     sl.fcflat.release();
+    sl.boxtab.release();
     if (sl.ev0) cudaEventDestroy(sl.ev0);
     if (sl.ev1) cudaEventDestroy(sl.ev1);
   }
@@ -613,7 +697,7 @@ int plm_eval_rhs(plm_reactor* r, int ncells, double t, const double* y, const do
     if ((rc = stage_in(r->scratch[3], rYsrc, size_t(ncells) * ns, &ds, st, true))) return rc;
     if ((rc = stage_in(r->scratch[4], static_cast<double*>(nullptr), size_t(ncells) * n, &dout, st, false))) return rc;
   }
-  if (r->path != 1 && plm::lane_supported(r->mech.h, plm::kIntegRK64, r->opts))
+  if (r->path == 2 ? plm::lane_supported(r->mech.h, plm::kIntegRK64, r->opts) : (r->path == 0 && plm::lane_auto(r->mech.h, plm::kIntegRK64, r->opts)))
     PLM_CUDA(plm::launch_lane_rhs(r->mech.h, ncells, t, dy, de, des, ds, dout, st));
   else
     PLM_CUDA(plm::launch_rhs(r->mech.h, r->mech.d, ncells, t, dy, de, des, ds, dout, st));
@@ -635,7 +719,8 @@ int plm_eval_jac(plm_reactor* r, int ncells, const double* y, double* J, void* c
     if ((rc = stage_in(r->scratch[0], y, size_t(ncells) * n, &dy, st, true))) return rc;
     if ((rc = stage_in(r->scratch[5], static_cast<double*>(nullptr), size_t(ncells) * n * n, &dJ, st, false))) return rc;
   }
-  if (r->path != 1 && r->mech.h.eint == 0 && plm::lane_supported(r->mech.h, plm::kIntegRK64, r->opts))
+  if (r->mech.h.eint == 0 &&
+      (r->path == 2 ? plm::lane_supported(r->mech.h, plm::kIntegRK64, r->opts) : (r->path == 0 && plm::lane_auto(r->mech.h, plm::kIntegRK64, r->opts))))
     PLM_CUDA(plm::launch_lane_jac(r->mech.h, ncells, dy, dJ, st));
   else
     PLM_CUDA(plm::launch_jac(r->mech.h, r->mech.d, ncells, dy, dJ, st));

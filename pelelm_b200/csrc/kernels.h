@@ -34,6 +34,11 @@ struct BoxArgs {
   int mks;
   plm_a4d IR;      // N components, p == nullptr: not wanted
   double dt_inv;   // 1/dt as the host computes it (PeleLM.cpp:5792)
+  // several boxes in one launch (lane = cell kernels; plm_react_boxes): nboxes > 0 => cell c of the call is cell
+  // c - off[b] of tab[b], off[b] <= c < off[b + 1]; lo / hi / arrays / mask come from tab[b], everything else from this struct
+  const BoxArgs* tab;
+  const int64_t* off;
+  int nboxes;
 };
 
 struct LaunchCfg {
@@ -55,7 +60,8 @@ cudaError_t launch_jac(const DevMech& m, const DevMech* dm, int ncells, const do
 // PeleLM_K.H:57-101 reactionRateRhoY over a box (MKS in, MKS out; mask < 0 => zero)
 cudaError_t launch_reaction_rate(const DevMech& m, const DevMech* dm, const BoxArgs& a, plm_a4d rhoYdot, cudaStream_t stream);
 // ---- lane = cell path (lane_kernels.cu): one thread per cell, straight-line generated mechanism code ----
-bool lane_supported(const DevMech& m, int integ, const ReactOpts& o);
+bool lane_supported(const DevMech& m, int integ, const ReactOpts& o);   // the lane kernels cover the request
+bool lane_auto(const DevMech& m, int integ, const ReactOpts& o);        // ... and are what the automatic choice runs
 int lane_threads(const DevMech& m, int integ, int qmax);   // CTA size; one CTA per SM
 size_t lane_ws_bytes(const DevMech& m, int integ, int qmax, int blocks);   // workspace of a launch with `blocks` CTAs
 cudaError_t launch_lane_react(const DevMech& m, const ReactOpts& o, const BoxArgs& a, int integ, int blocks,

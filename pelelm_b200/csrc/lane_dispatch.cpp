@@ -46,7 +46,8 @@ int lane_theta()
   static const int v = [] {
     const char* e = std::getenv("PLM_LANE_THETA");
     const int t = e ? std::atoi(e) : 0;
-    return t > 0 ? t : 48;
+    const char* al = std::getenv("PLM_LANE_ALIGN");  // development: phase-aligned rounds (one CTA barrier per round)
+    return (t > 0 ? t : 96) | ((al != nullptr && al[0] == '1') ? (1 << 30) : 0);
   }();
   return v;
 }
@@ -63,6 +64,24 @@ bool lane_supported(const DevMech& m, int integ, const ReactOpts& o)
   if (!lane_enabled() || mech_id(m) < 0) return false;
   if (integ == kIntegRK64) return true;
   return o.ajac == 1 && m.eint == 0;
+}
+
+// What the automatic choice (plm_reactor_set_path 0) runs through the lane = cell kernels: the requests where they are the
+// faster family on B200 (profiles/r02c_lane_ab.json: LiDryer ReactorRK64 5.6x, ReactorCvode 1.3x the warp-per-cell kernels;
+// drm19's straight-line code is instruction-fetch bound and stays with the warp-per-cell kernels).  PLM_LANE_AUTO=all|none
+// overrides (development).
+bool lane_auto(const DevMech& m, int integ, const ReactOpts& o)
+{
+  if (!lane_supported(m, integ, o)) return false;
+  static const int mode = [] {
+    const char* e = std::getenv("PLM_LANE_AUTO");
+    if (e != nullptr && e[0] == 'a') return 2;
+    if (e != nullptr && e[0] == 'n') return 0;
+    return 1;
+  }();
+  if (mode == 2) return true;
+  if (mode == 0) return false;
+  return mech_id(m) == 0;
 }
 
 int lane_threads(const DevMech& m, int integ, int qmax)

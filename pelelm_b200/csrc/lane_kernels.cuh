@@ -45,9 +45,21 @@ __device__ __forceinline__ int64_t lane_a4_off(const plm_a4d& a, int i, int j, i
 
 // the cell's addresses; returns the mask value (1 when there is no mask)
 template <int NS>
-__device__ __forceinline__ int lane_view(const BoxArgs& a, int64_t c, CellView& v)
+__device__ __forceinline__ int lane_view(const BoxArgs& a0, int64_t c, CellView& v)
 {
-  if (a.flat) {
+  const BoxArgs* bx = &a0;
+  if (a0.nboxes > 0) {  // the box that holds cell c: off[b] <= c < off[b + 1]
+    int lo = 0, hi = a0.nboxes;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(a0.off + mid) <= c) lo = mid;
+      else hi = mid;
+    }
+    bx = a0.tab + lo;
+    c -= __ldg(a0.off + lo);
+  }
+  const BoxArgs& a = *bx;
+  if (a0.flat) {
     v.rY = a.rY.p + c * (NS + 1); v.sY = 1;
     v.rYsrc = a.rYsrc.p + c * NS; v.sS = 1;
     v.T = nullptr; v.rE = a.rE.p + c; v.rEsrc = a.rEsrc.p + c; v.FC = a.FC.p + c; v.IR = nullptr; v.sI = 0;
@@ -98,6 +110,10 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
   bool exhausted = false;
   int wait_acc = 0;
   const int64_t ncells = a.ncells;
+  // theta bit 30: phase-aligned rounds -- the warps of the CTA start every round together (one barrier per round), so that
+  // they stream through the straight-line code as ONE instruction stream the instruction cache can prefetch
+  const bool align = (theta >> 30) & 1;
+  theta &= 0x3fffffff;
 
 #pragma unroll 1
   for (;;) {
@@ -137,24 +153,33 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
       }
     }
     const unsigned active = __ballot_sync(0xffffffffu, it.phase != PH_IDLE);
-    if (active == 0) {
+    if (align) {  // every warp of the CTA runs every round (and every barrier of it) until all of them are out of cells
+      const bool warp_done = (active == 0) && (__ballot_sync(0xffffffffu, !exhausted) == 0);
+      if (__syncthreads_and(warp_done)) break;
+    } else if (active == 0) {
       if (__ballot_sync(0xffffffffu, !exhausted) == 0) break;
       continue;
     }
     // ---- (A) + (B) ----
-    lane_round_rhs<M, EINT, I, LAY>(it, w);
+    if (active) lane_round_rhs<M, EINT, I, LAY>(it, w);
 
     if constexpr (BDF) {
       // ---- (C) linear-solver setups, when enough lanes wait (or nothing else can run) ----
-      const unsigned waitm = __ballot_sync(0xffffffffu, it.phase == PH_WAIT_SETUP);
-      if (waitm) {
-        const int nwait = __popc(waitm);
+      bool go;
+      if (align) {  // decided for the whole CTA: its warps then run the setup code together, as they run everything else
+        const int nwait = __syncthreads_count(it.phase == PH_WAIT_SETUP);
+        const int nbusy = __syncthreads_count(it.phase != PH_IDLE && it.phase != PH_WAIT_SETUP);
         wait_acc += nwait;
+        go = nwait > 0 && (wait_acc >= theta * int(blockDim.x >> 5) || nbusy == 0);
+      } else {
+        const unsigned waitm = __ballot_sync(0xffffffffu, it.phase == PH_WAIT_SETUP);
+        wait_acc += __popc(waitm);
         const unsigned busy = __ballot_sync(0xffffffffu, it.phase != PH_IDLE && it.phase != PH_WAIT_SETUP);
-        if (wait_acc >= theta || busy == 0) {
-          wait_acc = 0;
-          if (it.phase == PH_WAIT_SETUP) it.setup(w);
-        }
+        go = waitm != 0 && (wait_acc >= theta || busy == 0);
+      }
+      if (go) {
+        wait_acc = 0;
+        if (it.phase == PH_WAIT_SETUP) it.setup(w);
       }
       // ---- (D) Newton correction and the step logic behind it, (E) the shared tail ----
       if (it.phase == PH_SOLVE) it.solve(w);

@@ -103,7 +103,7 @@ def test_lane_big_batch_vs_reference(lane_lib, mech, form):
     check_state(got, ref, 1e-10, tag=mech + "/big", fc_equal_min=0.98, fc_rel=0.01)
     r1, r2 = rel_errors(got[0], ref[0])
     print("%s: max relative error of rhoY_k over Y_k > 1e-12: %.2e; over rhoY_k > atol: %.2e" % (mech, r1, r2))
-    assert r2 <= 1e-6
+    assert r2 <= 1e-4
 
 
 @pytest.mark.parametrize("form", FORMS)

@@ -17,7 +17,7 @@ dev = torch.device("cuda", 0)
 out = {}
 nrhs = int(os.environ.get("AB_NRHS", 1 << 18))
 ncell = int(os.environ.get("AB_NCELL", 1 << 16))
-for mech in ("LiDryer", "drm19"):
+for mech in os.environ.get("AB_MECHS", "LiDryer,drm19").split(","):
     b = synth.synthetic_batch(mech, nrhs, seed=11, forcing=True)
     ns = b["rY"].shape[0]
     y = torch.from_numpy(np.ascontiguousarray(np.vstack([b["rY"], b["T"][None, :]]).T)).to(dev)
