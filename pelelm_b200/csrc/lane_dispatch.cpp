@@ -47,7 +47,9 @@ int lane_theta()
     const char* e = std::getenv("PLM_LANE_THETA");
     const int t = e ? std::atoi(e) : 0;
     const char* al = std::getenv("PLM_LANE_ALIGN");  // development: phase-aligned rounds (one CTA barrier per round)
-    return (t > 0 ? t : 96) | ((al != nullptr && al[0] == '1') ? (1 << 30) : 0);
+    const char* co = std::getenv("PLM_LANE_COOP");   // development: warp-cooperative factorisations (lane_kernels.cuh)
+    // phase-aligned rounds are the default: LiDryer ReactorCvode 295 k -> 636 k cells*dt/s, drm19 62 k -> 165 k (profiles/r02d, r02e)
+    return (t > 0 ? t : 64) | ((al != nullptr && al[0] == '0') ? 0 : (1 << 30)) | ((co != nullptr && co[0] == '1') ? (1 << 29) : 0);
   }();
   return v;
 }

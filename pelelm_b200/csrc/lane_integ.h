@@ -86,11 +86,15 @@ struct LaneLay {
   static constexpr int EWT = ZN + (QM + 1) * N;
   static constexpr int ACOR = EWT + N;
   static constexpr int Y = ACOR + N;                  // argument of the right-hand side / result of the cell
-  static constexpr int F = Y + N;                     // last right-hand side; then the Newton right-hand side / correction,
+  // The straight-line right-hand side reads its argument into registers before it writes its result, and nothing reads the
+  // argument afterwards (a Jacobian is only ever evaluated at the first residual of a Newton attempt, where y = zn0): the
+  // result overwrites it.  The loop form reads y while it writes f.
+  static constexpr int F = M::kTable ? Y + N : Y;     // last right-hand side; then the Newton right-hand side / correction,
   static constexpr int DEL = F;                       // Newton right-hand side / correction (in place)
   static constexpr int SC = F + N;                    // table-driven kernels: concentrations [NS] and g/RT [NS] of the
   static constexpr int G = SC + NS;                   // right-hand side / Jacobian being evaluated
-  static constexpr int FAST_BDF = M::kTable ? G + NS : F + N;
+  static constexpr int SCAL = M::kTable ? G + NS : F + N;   // cvode's tau[QM+3], tq[6], l[QM+3]
+  static constexpr int FAST_BDF = SCAL + 2 * (QM + 3) + 6;
   static constexpr int RK_F = 3 * N, RK_SC = RK_F + N, RK_G = RK_SC + NS;   // RK64: soln, carry, err, (f, sc, g)
   static constexpr int FAST_RK = M::kTable ? RK_G + NS : 3 * N;
   // ---- BIG space ----
@@ -243,7 +247,9 @@ struct LaneBdf {
   int phase = PH_IDLE;
   // ---- per-cell scalars (cvode_impl.h CVodeMemRec) ----
   double tn, h, hprime, hscale, eta, etamax, tout, t0;
-  double tau[NT], tq[6], l[NT];
+  // cvode's tau[], tq[], l[] live in the FAST space (SCAL): as member arrays they are indexed dynamically, i.e. local
+  // memory, and with the SM's shared memory given to the vectors local memory is served by the L2
+  static constexpr int T_TAU = L::SCAL, T_TQ = L::SCAL + NT, T_L = L::SCAL + NT + 6;
   double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5, saved_t, dsm;
   double hg, hub, hlb, hsign;  // cvHin
   double rhoe_init, rhoesrc, hin_load, t_eval;
@@ -315,9 +321,9 @@ struct LaneBdf {
     saved_tq5 = 0.0;
     crate = 1.0; delp = 0.0; jcur = 0; eta = 1.0; qprime = 1;
 #pragma unroll
-    for (int i = 0; i < NT; ++i) tau[i] = l[i] = 0.0;
+    for (int i = 0; i < NT; ++i) w.d(T_TAU + i) = w.d(T_L + i) = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) tq[i] = 0.0;
+    for (int i = 0; i < 6; ++i) w.d(T_TQ + (i)) = 0.0;
 #pragma unroll(VU)
     for (int i = 0; i < N; ++i) zn(w, 0, i) = w.d(L::Y + i);
     if (!ewtset(w)) {  // CVode returns CV_ILL_INPUT before any work: the state is the input
@@ -440,18 +446,18 @@ struct LaneBdf {
   PLM_LHD void increase_bdf(const Ws& w)
   {
     double alpha0, alpha1, prod, xi, xiold, hsum, A1;
-    for (int i = 0; i <= qmax; i++) l[i] = 0.0;
-    l[2] = alpha1 = prod = xiold = 1.0;
+    for (int i = 0; i <= qmax; i++) w.d(T_L + (i)) = 0.0;
+    w.d(T_L + (2)) = alpha1 = prod = xiold = 1.0;
     alpha0 = -1.0;
     hsum = hscale;
     if (q > 1) {
       for (int j = 1; j < q; j++) {
-        hsum += tau[j + 1];
+        hsum += w.d(T_TAU + (j + 1));
         xi = hsum / hscale;
         prod *= xi;
         alpha0 -= 1.0 / (j + 1);
         alpha1 += 1.0 / xi;
-        for (int i = j + 2; i >= 2; i--) l[i] = l[i] * xiold + l[i - 1];
+        for (int i = j + 2; i >= 2; i--) w.d(T_L + (i)) = w.d(T_L + (i)) * xiold + w.d(T_L + (i - 1));
         xiold = xi;
       }
     }
@@ -462,24 +468,24 @@ struct LaneBdf {
     if (q > 1)
       for (int j = 2; j <= q; j++) {
 #pragma unroll(VU)
-        for (int i = 0; i < N; ++i) zn(w, j, i) = l[j] * zn(w, Lq, i) + zn(w, j, i);
+        for (int i = 0; i < N; ++i) zn(w, j, i) = w.d(T_L + (j)) * zn(w, Lq, i) + zn(w, j, i);
       }
   }
   PLM_LHD void decrease_bdf(const Ws& w)
   {
     double hsum, xi;
-    for (int i = 0; i <= qmax; i++) l[i] = 0.0;
-    l[2] = 1.0;
+    for (int i = 0; i <= qmax; i++) w.d(T_L + (i)) = 0.0;
+    w.d(T_L + (2)) = 1.0;
     hsum = 0.0;
     for (int j = 1; j <= q - 2; j++) {
-      hsum += tau[j];
+      hsum += w.d(T_TAU + (j));
       xi = hsum / hscale;
-      for (int i = j + 2; i >= 2; i--) l[i] = l[i] * xi + l[i - 1];
+      for (int i = j + 2; i >= 2; i--) w.d(T_L + (i)) = w.d(T_L + (i)) * xi + w.d(T_L + (i - 1));
     }
     if (q > 2)
       for (int j = 2; j < q; j++) {
 #pragma unroll(VU)
-        for (int i = 0; i < N; ++i) zn(w, j, i) = -l[j] * zn(w, q, i) + zn(w, j, i);
+        for (int i = 0; i < N; ++i) zn(w, j, i) = -w.d(T_L + (j)) * zn(w, q, i) + zn(w, j, i);
       }
   }
   PLM_LHD void predict(const Ws& w)
@@ -500,51 +506,51 @@ struct LaneBdf {
         for (int i = 0; i < N; ++i) zn(w, j - 1, i) = zn(w, j - 1, i) - zn(w, j, i);
       }
   }
-  PLM_LHD void set_bdf()
+  PLM_LHD void set_bdf(const Ws& w)
   {
     double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
-    l[0] = l[1] = xi_inv = xistar_inv = 1.0;
-    for (int i = 2; i <= q; i++) l[i] = 0.0;
+    w.d(T_L + (0)) = w.d(T_L + (1)) = xi_inv = xistar_inv = 1.0;
+    for (int i = 2; i <= q; i++) w.d(T_L + (i)) = 0.0;
     alpha0 = alpha0_hat = -1.0;
     hsum = h;
     if (q > 1) {
       for (int j = 2; j < q; j++) {
-        hsum += tau[j - 1];
+        hsum += w.d(T_TAU + (j - 1));
         xi_inv = h / hsum;
         alpha0 -= 1.0 / j;
-        for (int i = j; i >= 1; i--) l[i] += l[i - 1] * xi_inv;
+        for (int i = j; i >= 1; i--) w.d(T_L + (i)) += w.d(T_L + (i - 1)) * xi_inv;
       }
       alpha0 -= 1.0 / q;
-      xistar_inv = -l[1] - alpha0;
-      hsum += tau[q - 1];
+      xistar_inv = -w.d(T_L + (1)) - alpha0;
+      hsum += w.d(T_TAU + (q - 1));
       xi_inv = h / hsum;
-      alpha0_hat = -l[1] - xi_inv;
-      for (int i = q; i >= 1; i--) l[i] += l[i - 1] * xistar_inv;
+      alpha0_hat = -w.d(T_L + (1)) - xi_inv;
+      for (int i = q; i >= 1; i--) w.d(T_L + (i)) += w.d(T_L + (i - 1)) * xistar_inv;
     }
     // cvSetTqBDF
     double A1, A2, A3, A4, A5, A6, C, Cpinv, Cppinv;
     A1 = 1.0 - alpha0_hat + alpha0;
     A2 = 1.0 + q * A1;
-    tq[2] = lane_fabs(A1 / (alpha0 * A2));
-    tq[5] = lane_fabs(A2 * xistar_inv / (l[q] * xi_inv));
+    w.d(T_TQ + (2)) = lane_fabs(A1 / (alpha0 * A2));
+    w.d(T_TQ + (5)) = lane_fabs(A2 * xistar_inv / (w.d(T_L + (q)) * xi_inv));
     if (qwait == 1) {
       if (q > 1) {
-        C = xistar_inv / l[q];
+        C = xistar_inv / w.d(T_L + (q));
         A3 = alpha0 + 1.0 / q;
         A4 = alpha0_hat + xi_inv;
         Cpinv = (1.0 - A4 + A3) / A3;
-        tq[1] = lane_fabs(C * Cpinv);
+        w.d(T_TQ + (1)) = lane_fabs(C * Cpinv);
       } else
-        tq[1] = 1.0;
-      hsum += tau[q];
+        w.d(T_TQ + (1)) = 1.0;
+      hsum += w.d(T_TAU + (q));
       xi_inv = h / hsum;
       A5 = alpha0 - (1.0 / (q + 1));
       A6 = alpha0_hat - xi_inv;
       Cppinv = (1.0 - A6 + A5) / A2;
-      tq[3] = lane_fabs(Cppinv / (xi_inv * (q + 2) * A5));
+      w.d(T_TQ + (3)) = lane_fabs(Cppinv / (xi_inv * (q + 2) * A5));
     }
-    tq[4] = cv::CORTES / tq[2];
-    rl1 = 1.0 / l[1];
+    w.d(T_TQ + (4)) = cv::CORTES / w.d(T_TQ + (2));
+    rl1 = 1.0 / w.d(T_L + (1));
     gamma = h * rl1;
     if (nst == 0) gammap = gamma;
     gamrat = (nst > 0) ? gamma / gammap : 1.0;
@@ -602,7 +608,7 @@ struct LaneBdf {
     if (pend & P_RESCALE) rescale(w);
     if (pend & P_ATTEMPT) {  // top of cvStep's retry loop up to the first residual of the Newton iteration
       predict(w);
-      set_bdf();
+      set_bdf(w);
       convfail = ((nflag == cv::FIRST_CALL) || (nflag == cv::PREV_ERR_FAIL)) ? cv::CV_NO_FAILURES : cv::CV_FAIL_OTHER;
       call_setup = (nflag == cv::PREV_CONV_FAIL) || (nflag == cv::PREV_ERR_FAIL) || (nst == 0) ||
                    (nst >= nstlp + cv::MSBP) || (lane_fabs(gamrat - 1.0) > cv::DGMAX_LSETUP);
@@ -661,6 +667,7 @@ struct LaneBdf {
         for (int i = 0; i < N; ++i) w.d(L::F + i) = f[i];
         if (first_res && call_setup) {
           if (jbad) convfail = cv::CV_FAIL_BAD_J;
+          setup_decide();
           phase = PH_WAIT_SETUP;
         } else {
           if (first_res) mnewt = 0;
@@ -680,29 +687,37 @@ struct LaneBdf {
     int off;
     PLM_LHD double& operator()(int r, int c) const { return w.g(off + c * N + r); }
   };
-  PLM_LHD void setup(const Ws& w)
+  // The setup in three pieces, so that the kernel can run them at different granularities: setup_decide when the lane starts
+  // to wait (does it need a fresh Jacobian?), setup_jac for the lanes that do (lane-parallel straight-line code, batched),
+  // then the factorisation -- getrf() below per lane, or the warp-cooperative one of lane_kernels.cuh per cell -- and
+  // setup_finish.  setup() is all of it for one lane (host model; fallback).
+  int need_jac = 0;
+  PLM_LHD void setup_decide()
   {
     const double dgamma = lane_fabs((gamma / gammap) - 1.0);
     const bool jb = (nst == 0) || (nst >= nstlj + msbj) || ((convfail == cv::CV_FAIL_BAD_J) && (dgamma < cv::DGMAX_JBAD)) ||
                     (convfail == cv::CV_FAIL_OTHER);
-    if (jb) {
-      jcur = 1;
-      JAcc ja{w, L::SAV};
-      if constexpr (M::kTable) {
-        lt_cjac<M>(LV{&w.d(L::Y)}, ja, LV{&w.d(L::SC)}, LV{&w.d(L::G)}, LV{&w.g(L::JSCR)}, LV{&w.g(L::JSCR + NS)},
-                   LV{&w.g(L::JSCR + 2 * NS)}, LV{&w.g(L::JSCR + 3 * NS)});
-      } else {
-        double y[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) y[i] = w.d(L::Y + i);
-        lane_cjac<M>(y, ja);
-      }
-      nje++;
-      nstlj = nst;
+    jcur = jb ? 1 : 0;
+    need_jac = jcur;
+  }
+  PLM_LHD void setup_jac(const Ws& w)
+  {
+    JAcc ja{w, L::SAV};
+    if constexpr (M::kTable) {
+      lt_cjac<M>(LV{&w.d(L::ZN)}, ja, LV{&w.d(L::SC)}, LV{&w.d(L::G)}, LV{&w.g(L::JSCR)}, LV{&w.g(L::JSCR + NS)},
+                 LV{&w.g(L::JSCR + 2 * NS)}, LV{&w.g(L::JSCR + 3 * NS)});
     } else {
-      jcur = 0;
+      double y[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = zn(w, 0, i);  // = y of the residual just evaluated (acor = 0)
+      lane_cjac<M>(y, ja);
     }
-    const int ier = getrf(w);
+    nje++;
+    nstlj = nst;
+    need_jac = 0;
+  }
+  PLM_LHD void setup_finish(int ier)
+  {
     nsetups++;
     gamrat = 1.0;
     gammap = gamma;
@@ -716,6 +731,12 @@ struct LaneBdf {
     }
     mnewt = 0;
     phase = PH_SOLVE;
+  }
+  PLM_LHD void setup(const Ws& w)
+  {
+    setup_decide();
+    if (need_jac) setup_jac(w);
+    setup_finish(getrf(w));
   }
   // A = I - gamma J (cvLsLinSys) and denseGETRF (partial pivoting, first maximum) in ONE pass over the saved Jacobian,
   // column by column ("left-looking"): column j is formed in the FAST space, receives the updates of the finished columns
@@ -850,7 +871,7 @@ struct LaneBdf {
       const double r = del / delp;
       crate = (cv::CRDOWN * crate > r) ? cv::CRDOWN * crate : r;
     }
-    const double dcon = del * ((1.0 < crate) ? 1.0 : crate) / tq[4];
+    const double dcon = del * ((1.0 < crate) ? 1.0 : crate) / w.d(T_TQ + (4));
     if (dcon <= 1.0) {
       acnrm = (mnewt == 0) ? del : sqrt(suma / N);
       nls_success(w);
@@ -894,7 +915,7 @@ struct LaneBdf {
   PLM_LHD void nls_success(const Ws& w)
   {
     jcur = 0;
-    dsm = acnrm * tq[2];
+    dsm = acnrm * w.d(T_TQ + (2));
     if (dsm > 1.0) {
       nef++;
       netf++;
@@ -926,7 +947,7 @@ struct LaneBdf {
     prepare_next_step(w);
     etamax = (nst <= cv::SMALL_NST) ? cv::ETA_MAX_ES : cv::ETA_MAX_GS;
 #pragma unroll(VU)
-    for (int i = 0; i < N; ++i) w.d(L::ACOR + i) *= tq[2];
+    for (int i = 0; i < N; ++i) w.d(L::ACOR + i) *= w.d(T_TQ + (2));
     nstloc++;
     if ((tn - tout) * h >= 0.0) {
       // CVodeGetDky(tout, 0): N_VLinearCombination over zn[q..0] with s^j
@@ -951,18 +972,18 @@ struct LaneBdf {
   PLM_LHD void complete_step(const Ws& w)
   {
     nst++;
-    for (int i = q; i >= 2; i--) tau[i] = tau[i - 1];
-    if ((q == 1) && (nst > 1)) tau[2] = tau[1];
-    tau[1] = h;
+    for (int i = q; i >= 2; i--) w.d(T_TAU + (i)) = w.d(T_TAU + (i - 1));
+    if ((q == 1) && (nst > 1)) w.d(T_TAU + (2)) = w.d(T_TAU + (1));
+    w.d(T_TAU + (1)) = h;
     for (int j = 0; j <= q; j++) {
 #pragma unroll(VU)
-      for (int i = 0; i < N; ++i) zn(w, j, i) = l[j] * w.d(L::ACOR + i) + zn(w, j, i);
+      for (int i = 0; i < N; ++i) zn(w, j, i) = w.d(T_L + (j)) * w.d(L::ACOR + i) + zn(w, j, i);
     }
     qwait--;
     if ((qwait == 1) && (q != qmax)) {
 #pragma unroll(VU)
       for (int i = 0; i < N; ++i) zn(w, qmax, i) = w.d(L::ACOR + i);
-      saved_tq5 = tq[5];
+      saved_tq5 = w.d(T_TQ + (5));
     }
   }
   PLM_LHD void set_eta()
@@ -995,15 +1016,15 @@ struct LaneBdf {
     qwait = 2;
     double etaqm1 = 0.0;
     if (q > 1) {
-      const double ddn = wrms(w, L::ZN + q * N) * tq[1];
+      const double ddn = wrms(w, L::ZN + q * N) * w.d(T_TQ + (1));
       etaqm1 = 1.0 / (rpowR(cv::BIAS1 * ddn, q) + cv::ADDON);
     }
     double etaqp1 = 0.0;
     if (q != qmax && saved_tq5 != 0.0) {
-      double rp = 1.0;  // SUNRpowerI(h / tau[2], L)
-      const double base = h / tau[2];
+      double rp = 1.0;  // SUNRpowerI(h / w.d(T_TAU + (2)), L)
+      const double base = h / w.d(T_TAU + (2));
       for (int i = 1; i <= Lq; i++) rp *= base;
-      const double cquot = (tq[5] / saved_tq5) * rp;
+      const double cquot = (w.d(T_TQ + (5)) / saved_tq5) * rp;
       double sum = 0.0;
 #pragma unroll(VU)
       for (int i = 0; i < N; ++i) {
@@ -1011,7 +1032,7 @@ struct LaneBdf {
         const double p = tv * w.d(L::EWT + i);
         sum += p * p;
       }
-      const double dup = sqrt(sum / N) * tq[3];
+      const double dup = sqrt(sum / N) * w.d(T_TQ + (3));
       etaqp1 = 1.0 / (rpowR(cv::BIAS3 * dup, Lq + 1) + cv::ADDON);
     }
     double etam = (etaq > etaqp1) ? etaq : etaqp1;

@@ -29,7 +29,8 @@ template <class I, class LAY>
 struct LaneShape {
   static constexpr int FAST = I::kBdf ? LAY::FAST_BDF : LAY::FAST_RK;
   static constexpr int BIG = I::kBdf ? LAY::BIG_BDF : LAY::BIG_RK;
-  static constexpr int WARP_BYTES = FAST * 32 * 8;
+  static constexpr int LUA = I::kBdf ? LAY::N * (LAY::N + 1) : 0;   // per warp: one cell's Newton matrix (cooperative LU)
+  static constexpr int WARP_BYTES = (FAST * 32 + LUA) * 8;
   static constexpr int FIT = (227 * 1024 - 1024) / WARP_BYTES;
   static constexpr int WARPS = FIT >= 8 ? 8 : FIT;
   static constexpr int THREADS = WARPS * 32;
@@ -80,6 +81,70 @@ __device__ __forceinline__ int lane_view(const BoxArgs& a0, int64_t c, CellView&
   return 1;
 }
 
+// Warp-cooperative factorisation of ONE cell's Newton matrix: A = I - gamma J (cvLsLinSys) and denseGETRF (partial pivoting,
+// first maximum: sundials_dense.c:135-196) with lane = row, the matrix in shared memory (leading dimension odd: rows are
+// swept conflict-free).  Every element receives the updates A[i][j] -= A[k][j] * L[i][k] in the order k = 0, 1, ... with the
+// operands of the serial routine, so the factors are bit-identical to LaneBdf::getrf.  `big` = the BIG space of the cell
+// (lane offset included): saved Jacobian in, LU factors and pivot rows out.  Returns denseGETRF's flag (0 or k + 1).
+// A lane-parallel LU costs the same instructions whether 2 or 32 lanes of the warp need one; a linear-solver setup is
+// wanted by ~6 % of the lanes per round, so the warp serves them one cell at a time, 22 lanes wide, as soon as they ask.
+template <class LAY>
+__device__ __forceinline__ int coop_getrf(double* __restrict__ A, double* __restrict__ big, double gamma, int lane)
+{
+  constexpr int N = LAY::N, LD = (N % 2 == 0) ? N + 1 : N;
+  const double c = -gamma;
+  for (int e = lane; e < N * N; e += 32) {
+    const int col = e / N, row = e - col * N;
+    double a = big[size_t(LAY::SAV + e) * 32] * c;
+    if (row == col) a += 1.0;
+    A[row * LD + col] = a;
+  }
+  __syncwarp();
+  int ier = 0;
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    // pivot: first row >= k with the largest |a_ik| (non-negative doubles order like their bit patterns)
+    const bool mine = lane >= k && lane < N;
+    const double av = mine ? fabs(A[lane * LD + k]) : 0.0;
+    const unsigned hi = mine ? unsigned(__double2hiint(av)) : 0u, lo = unsigned(__double2loint(av));
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, (mine && hi == mhi) ? lo : 0u);
+    const unsigned cand = __ballot_sync(0xffffffffu, mine && hi == mhi && lo == mlo);
+    const int p = cand ? __ffs(cand) - 1 : k;
+    if (lane == 0) big[size_t(LAY::PERM + k) * 32] = double(p);
+    if (A[p * LD + k] == 0.0) {
+      ier = k + 1;
+      break;
+    }
+    if (p != k && lane < N) {  // lane = column
+      const double t = A[k * LD + lane];
+      A[k * LD + lane] = A[p * LD + lane];
+      A[p * LD + lane] = t;
+    }
+    __syncwarp();
+    const double akk = A[k * LD + k];
+    const double mult = (fabs(akk) > 1e-280 && fabs(akk) < 1e280) ? frcp(akk) : 1.0 / akk;  // ONE / col_k[k]
+    if (lane > k && lane < N) {
+      double* row = A + lane * LD;
+      const double lik = row[k] * mult;
+      row[k] = lik;
+      const double* rk = A + k * LD;
+#pragma unroll 2
+      for (int j = k + 1; j < N; ++j) {
+        const double a_kj = rk[j];
+        if (a_kj != 0.0) row[j] -= a_kj * lik;
+      }
+    }
+    __syncwarp();
+  }
+  for (int e = lane; e < N * N; e += 32) {
+    const int col = e / N, row = e - col * N;
+    big[size_t(LAY::MAT + e) * 32] = A[row * LD + col];
+  }
+  __syncwarp();
+  return ier;
+}
+
 template <class M, class I, class LAY, int EINT>
 __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
     lane_react_kernel(const ReactOpts ro, const BoxArgs a, unsigned long long* __restrict__ counter,
@@ -89,7 +154,8 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
   constexpr bool BDF = I::kBdf;
   using SH = LaneShape<I, LAY>;
   extern __shared__ double lane_smem[];
-  double* s_typ = lane_smem + SH::WARPS * SH::FAST * 32;
+  double* s_typ = lane_smem + SH::WARPS * (SH::FAST * 32 + SH::LUA);
+  double* lu_scratch = lane_smem + SH::WARPS * SH::FAST * 32 + size_t(threadIdx.x >> 5) * SH::LUA;
   for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) s_typ[i] = ro.typ_vals[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -113,7 +179,11 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
   // theta bit 30: phase-aligned rounds -- the warps of the CTA start every round together (one barrier per round), so that
   // they stream through the straight-line code as ONE instruction stream the instruction cache can prefetch
   const bool align = (theta >> 30) & 1;
-  theta &= 0x3fffffff;
+  // theta bit 29 (development, PLM_LANE_COOP=1): factorisations warp-cooperative, one cell at a time, as soon as a lane asks,
+  // instead of lane-parallel when enough lanes wait.  Measured on B200 (profiles/r02f_*): 19 % fewer instructions, but the
+  // warps of a CTA then carry different numbers of factorisations per round and wait for each other: drm19 -12 %, LiDryer -25 %.
+  const bool coop = (theta >> 29) & 1;
+  theta &= 0x1fffffff;
 
 #pragma unroll 1
   for (;;) {
@@ -164,22 +234,39 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
     if (active) lane_round_rhs<M, EINT, I, LAY>(it, w);
 
     if constexpr (BDF) {
-      // ---- (C) linear-solver setups, when enough lanes wait (or nothing else can run) ----
+      // ---- (C) linear-solver setups.  Fresh Jacobians (lane-parallel straight-line code) when enough lanes want one, or
+      //      nothing else can run; factorisations (warp-cooperative, one cell at a time) as soon as a lane asks ----
       bool go;
+      const bool wants = it.phase == PH_WAIT_SETUP && (!coop || it.need_jac);
       if (align) {  // decided for the whole CTA: its warps then run the setup code together, as they run everything else
-        const int nwait = __syncthreads_count(it.phase == PH_WAIT_SETUP);
-        const int nbusy = __syncthreads_count(it.phase != PH_IDLE && it.phase != PH_WAIT_SETUP);
+        const int nwait = __syncthreads_count(wants);
+        const int nbusy = __syncthreads_count(it.phase != PH_IDLE && !wants);
         wait_acc += nwait;
         go = nwait > 0 && (wait_acc >= theta * int(blockDim.x >> 5) || nbusy == 0);
       } else {
-        const unsigned waitm = __ballot_sync(0xffffffffu, it.phase == PH_WAIT_SETUP);
+        const unsigned waitm = __ballot_sync(0xffffffffu, wants);
         wait_acc += __popc(waitm);
-        const unsigned busy = __ballot_sync(0xffffffffu, it.phase != PH_IDLE && it.phase != PH_WAIT_SETUP);
+        const unsigned busy = __ballot_sync(0xffffffffu, it.phase != PH_IDLE && !wants);
         go = waitm != 0 && (wait_acc >= theta || busy == 0);
       }
       if (go) {
         wait_acc = 0;
-        if (it.phase == PH_WAIT_SETUP) it.setup(w);
+        if (wants) {
+          if (it.need_jac) it.setup_jac(w);
+          if (!coop) it.setup_finish(it.getrf(w));
+        }
+      }
+      if (coop) {
+        unsigned lum = __ballot_sync(0xffffffffu, it.phase == PH_WAIT_SETUP && !it.need_jac);
+        int my_ier = 0;
+        while (lum) {
+          const int l = __ffs(lum) - 1;
+          lum &= lum - 1;
+          const double gam = __shfl_sync(0xffffffffu, it.gamma, l);
+          const int ier = coop_getrf<LAY>(lu_scratch, w.big - lane + l, gam, lane);
+          if (lane == l) my_ier = ier;
+        }
+        if (it.phase == PH_WAIT_SETUP && !it.need_jac) it.setup_finish(my_ier);
       }
       // ---- (D) Newton correction and the step logic behind it, (E) the shared tail ----
       if (it.phase == PH_SOLVE) it.solve(w);

@@ -463,7 +463,8 @@ def test_amr_levels_vs_port(capi, port_lib):
         if step == 0:
             fine_first = {b: bx["I_R"].clone() for b, bx in dev[2].data.items()}
     torch.cuda.synchronize()
-    assert adv.launches[0] == nsteps * sum(len(L.boxes) for L in dev)
+    # one launch per box (warp-per-cell kernels) or one per level (lane = cell kernels: plm_react_boxes)
+    assert adv.launches[0] in (nsteps * sum(len(L.boxes) for L in dev), nsteps * len(dev))
     assert not R.cell_status(box ** 3).any()
     R.close()
     # level 1's covered cells after its 3rd advance = mean of level 2's OLD I_R at that moment = level 2's 1st result
