@@ -44,6 +44,7 @@ PLM_LNOINL double lane_get_T_guarded(double hin, const double (&Y)[M::NS], doubl
     }
     t1 += dt;
     fresh = false;
+    if (t1 != t1) break;  // NaN: the reference iterates 200 times on it and returns NaN; same result, no work
   }
   if (!fresh) M::template mix_hc<EINT>(t1, Y, h1, c);
   c_out = c;
@@ -75,6 +76,7 @@ PLM_LHD double lane_get_T(double hin, const double (&Y)[M::NS], double Tguess, d
       }
       t1 += dt;
       fresh = false;
+      if (t1 != t1) break;  // NaN: the reference iterates 200 times on it and returns NaN; same result, no work
     }
     ok = (t1 >= tmin && t1 <= tmax);
     if (ok && !fresh) M::template mix_hc<EINT>(t1, Y, h1, c);
@@ -105,6 +107,12 @@ PLM_LHD double lane_rhs(const double (&y)[M::N], double (&ydot)[M::N], double hi
   double c;
   const double T = lane_get_T<M, EINT>(nrg, massfrac, y[ns], c);
   if (only_T) return T;
+  if (T != T) {  // a NaN state (the explicit integrator blew up): every component of the reference's result is NaN as well;
+                 // skip the rates instead of dragging the other 31 cells of the warp through the library's NaN paths
+#pragma unroll
+    for (int k = 0; k <= ns; ++k) ydot[k] = T;
+    return T;
+  }
   double sc[ns], wdot[ns];
 #pragma unroll
   for (int k = 0; k < ns; ++k) sc[k] = (rho * massfrac[k] * M::imw_of(k)) * 1.0e6;  // CKYTCR :2403, CKWC :4911

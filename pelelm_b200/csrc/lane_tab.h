@@ -88,6 +88,7 @@ PLM_LNOINL double lt_get_T_guarded(double hin, const V& y, double rho_inv, doubl
     }
     t1 += dt;
     fresh = false;
+    if (t1 != t1) break;  // NaN: the reference iterates 200 times on it and returns NaN; same result, no work
   }
   if (!fresh) lt_mix_hc<M, EINT>(t1, y, rho_inv, h1, c);
   c_out = c;
@@ -120,6 +121,7 @@ PLM_LHD double lt_get_T(double hin, const V& y, double rho_inv, double Tguess, d
       }
       t1 += dt;
       fresh = false;
+      if (t1 != t1) break;  // NaN: the reference iterates 200 times on it and returns NaN; same result, no work
     }
     ok = (t1 >= tmin && t1 <= tmax);
     if (ok && !fresh) lt_mix_hc<M, EINT>(t1, y, rho_inv, h1, c);
@@ -244,6 +246,11 @@ PLM_LHD double lt_rhs(const V& y, const V& f, const V& sc, const V& g, double hi
   double c;
   const double T = lt_get_T<M, EINT>(nrg, y, rho_inv, y(ns), c);
   if (only_T) return T;
+  if (T != T) {  // a NaN state: every component of the reference's result is NaN as well
+#pragma unroll 1
+    for (int k = 0; k <= ns; ++k) f(k) = T;
+    return T;
+  }
 #pragma unroll 1
   for (int k = 0; k < ns; ++k) sc(k) = (rho * (y(k) * rho_inv) * M::imw(k)) * 1.0e6;  // CKYTCR :2403, CKWC :4911
   lt_production_rate<M>(f, sc, g, T);
