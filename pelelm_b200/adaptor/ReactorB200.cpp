@@ -122,8 +122,10 @@ int ReactorB200Common::b200_react_box(
   BL_PROFILE("Pele::ReactorB200::react()");
   b200_abort_on_failed_cells();  // of the calls before this one (a GPU build only enqueues; PeleLM syncs the stream per box)
   check(plm_reactor_set_typ_vals(m_handle, typ_vals.data(), NUM_SPECIES + 1), "plm_reactor_set_typ_vals");
-  const int lo[3] = {box.smallEnd(0), box.smallEnd(1), box.smallEnd(2)};
-  const int hi[3] = {box.bigEnd(0), box.bigEnd(1), box.bigEnd(2)};
+  // Dim3 bounds: a 2-D build (Exec/RegTests/FlameSheet) has two-component IntVects and Array4s with k = 0 only
+  const amrex::Dim3 blo = amrex::lbound(box), bhi = amrex::ubound(box);
+  const int lo[3] = {blo.x, blo.y, blo.z};
+  const int hi[3] = {bhi.x, bhi.y, bhi.z};
   const int rc = plm_react_box(
     m_handle, lo, hi, to_a4<amrex::Real, plm_a4d>(rY_in), to_a4<amrex::Real, plm_a4d>(rYsrc_in),
     to_a4<amrex::Real, plm_a4d>(T_in), to_a4<amrex::Real, plm_a4d>(rEner_in),

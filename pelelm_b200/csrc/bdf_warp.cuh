@@ -194,7 +194,9 @@ __device__ __noinline__ int gjinv_warp()
             p = rk2[j];
             r = row2[j];
 #else
-            const int jn = j + 1;  // the last iteration reads one pair past the row: the next row, or the pad behind the matrix
+            // the last iteration re-reads its own pair (not the pair past the row, which belongs to another lane's row: an
+            // unused value, but a read racecheck rightly reports)
+            const int jn = (j + 1 < n / 2) ? j + 1 : j;
 #endif
             const double2 pn = rk2[jn], rn = row2[jn];
             r.x -= p.x * f;
@@ -370,11 +372,13 @@ __device__ __noinline__ int gjinv2_warp()
       const double2* p2 = reinterpret_cast<const double2*>(rk);
       const double2* q2 = reinterpret_cast<const double2*>(rq);
       double2* r0 = reinterpret_cast<double2*>(row0);
-      double2* r1 = reinterpret_cast<double2*>(row1);
+      // a lane without a second row reads the pivot row instead (read-only during the sweep; its b is never stored): the
+      // clamped row n-1 is being written by its owner meanwhile, an unused value but a read racecheck rightly reports
+      double2* r1 = has1 ? reinterpret_cast<double2*>(row1) : const_cast<double2*>(p2);
       double2 p = p2[0], q = q2[0], a = r0[0], b = r1[0];
 #pragma unroll 3
       for (int j = 0; j < n / 2; ++j) {
-        const int jn = j + 1;  // the last iteration reads one pair past the row: the next row, or the pad behind the matrix
+        const int jn = (j + 1 < n / 2) ? j + 1 : j;  // the last iteration re-reads its own pair, not another lane's row
         const double2 pn = p2[jn], qn = q2[jn], an = r0[jn], bn = r1[jn];
         a.x = fma(-q.x, fB0, fma(-p.x, fA0, a.x));
         a.y = fma(-q.y, fB0, fma(-p.y, fA0, a.y));
@@ -460,6 +464,49 @@ __device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::
 // through references, so that only a handful of registers are live across the right-hand-side call. The first version
 // kept it all in registers: ~90 live values across a call into a function that needs ~120 registers itself, i.e. spills
 // around every call at 128 registers per thread and no way to run more than 16 warps per SM.
+// A warp-uniform scalar of the integrator in the warp's shared-memory area: every lane reads it, lane 0 alone writes it,
+// with a warp barrier on both sides of the store.  Round 1 let all 32 lanes store the same bits with no barrier ("benign"
+// races, 58 racecheck hazards): correct with today's code generation, but not by the CUDA memory model.
+template <class T>
+struct WScalar {
+  T* p;
+  __device__ __forceinline__ operator T() const { return *p; }
+  __device__ __forceinline__ const WScalar& operator=(T v) const
+  {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) *p = v;
+    __syncwarp();
+    return *this;
+  }
+  // store of a GROUP of scalars: the caller brackets the group with one pair of __syncwarp() (every value of the group is
+  // computed into registers first, so nothing inside the group reads what the group writes)
+  __device__ __forceinline__ void put(T v) const
+  {
+    if ((threadIdx.x & 31) == 0) *p = v;
+  }
+  __device__ __forceinline__ const WScalar& operator=(const WScalar& o) const { return *this = T(o); }
+  __device__ __forceinline__ const WScalar& operator+=(T v) const { return *this = T(*p + v); }
+  __device__ __forceinline__ const WScalar& operator-=(T v) const { return *this = T(*p - v); }
+  __device__ __forceinline__ const WScalar& operator*=(T v) const { return *this = T(*p * v); }
+  __device__ __forceinline__ T operator++(int) const
+  {
+    const T old = *p;
+    *this = T(old + 1);
+    return old;
+  }
+  __device__ __forceinline__ T operator--(int) const
+  {
+    const T old = *p;
+    *this = T(old - 1);
+    return old;
+  }
+};
+template <class T>
+struct WArray {
+  T* p;
+  __device__ __forceinline__ WScalar<T> operator[](int i) const { return WScalar<T>{p + i}; }
+};
+
 template <class L>
 struct BdfWarp {
   static constexpr int NSLOT = L::NSLOT, n = L::N, NP = L::NP, QM = L::QM, ld = L::LD;
@@ -475,27 +522,27 @@ struct BdfWarp {
   double* const Jsave;  // [n*ld] per-warp global scratch
   const LaneVec atolv, ewt, acor;
   double yv[NSLOT], ft[NSLOT], dl[NSLOT], tv[NSLOT];  // short-lived temporaries
-  double (&tau)[6], (&lc)[6], (&tq)[6];
-  double &tn, &h, &hprime, &hscale, &eta, &etamax;
-  double &rl1, &gamma, &gammap, &gamrat, &crate, &delp, &acnrm, &saved_tq5;
-  int &q, &qprime, &L_, &qwait, &indx_acor;
-  int &nst, &nfe, &ncfn, &netf, &nni, &nsetups, &nje, &nstlp, &nstlj;
-  int &jcur, &convfail;
+  const WArray<double> tau, lc, tq;
+  const WScalar<double> tn, h, hprime, hscale, eta, etamax;
+  const WScalar<double> rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
+  const WScalar<int> q, qprime, L_, qwait, indx_acor;
+  const WScalar<int> nst, nfe, ncfn, netf, nni, nsetups, nje, nstlp, nstlj;
+  const WScalar<int> jcur, convfail;
 
   __device__ __forceinline__ double* sc() const { return wb + L::SM; }
   __device__ __forceinline__ int* si() const { return reinterpret_cast<int*>(wb + L::SM + SC_I); }
+  static __device__ __forceinline__ int* sip(double* w) { return reinterpret_cast<int*>(w + L::SM + SC_I); }
   __device__ BdfWarp(const BdfOpts& o_, int lane_, double* wb_, double* js)
       : o(o_), lane(lane_), wb(wb_), Jsave(js),
         atolv{wb_ + L::ATOL + lane_}, ewt{wb_ + L::EWT + lane_}, acor{wb_ + L::ACOR + lane_},
-        tau(*reinterpret_cast<double(*)[6]>(wb_ + L::SM + SC_TAU)), lc(*reinterpret_cast<double(*)[6]>(wb_ + L::SM + SC_LC)),
-        tq(*reinterpret_cast<double(*)[6]>(wb_ + L::SM + SC_TQ)),
-        tn(sc()[SC_D + 0]), h(sc()[SC_D + 1]), hprime(sc()[SC_D + 2]), hscale(sc()[SC_D + 3]), eta(sc()[SC_D + 4]),
-        etamax(sc()[SC_D + 5]), rl1(sc()[SC_D + 6]), gamma(sc()[SC_D + 7]), gammap(sc()[SC_D + 8]),
-        gamrat(sc()[SC_D + 9]), crate(sc()[SC_D + 10]), delp(sc()[SC_D + 11]), acnrm(sc()[SC_D + 12]),
-        saved_tq5(sc()[SC_D + 13]),
-        q(si()[0]), qprime(si()[1]), L_(si()[2]), qwait(si()[3]), indx_acor(si()[4]), nst(si()[5]), nfe(si()[6]),
-        ncfn(si()[7]), netf(si()[8]), nni(si()[9]), nsetups(si()[10]), nje(si()[11]), nstlp(si()[12]), nstlj(si()[13]),
-        jcur(si()[14]), convfail(si()[15])
+        tau{wb_ + L::SM + SC_TAU}, lc{wb_ + L::SM + SC_LC}, tq{wb_ + L::SM + SC_TQ},
+        tn{wb_ + L::SM + SC_D + 0}, h{wb_ + L::SM + SC_D + 1}, hprime{wb_ + L::SM + SC_D + 2}, hscale{wb_ + L::SM + SC_D + 3},
+        eta{wb_ + L::SM + SC_D + 4}, etamax{wb_ + L::SM + SC_D + 5}, rl1{wb_ + L::SM + SC_D + 6}, gamma{wb_ + L::SM + SC_D + 7},
+        gammap{wb_ + L::SM + SC_D + 8}, gamrat{wb_ + L::SM + SC_D + 9}, crate{wb_ + L::SM + SC_D + 10},
+        delp{wb_ + L::SM + SC_D + 11}, acnrm{wb_ + L::SM + SC_D + 12}, saved_tq5{wb_ + L::SM + SC_D + 13},
+        q{sip(wb_) + 0}, qprime{sip(wb_) + 1}, L_{sip(wb_) + 2}, qwait{sip(wb_) + 3}, indx_acor{sip(wb_) + 4}, nst{sip(wb_) + 5},
+        nfe{sip(wb_) + 6}, ncfn{sip(wb_) + 7}, netf{sip(wb_) + 8}, nni{sip(wb_) + 9}, nsetups{sip(wb_) + 10}, nje{sip(wb_) + 11},
+        nstlp{sip(wb_) + 12}, nstlj{sip(wb_) + 13}, jcur{sip(wb_) + 14}, convfail{sip(wb_) + 15}
   {
   }
 
@@ -509,6 +556,7 @@ struct BdfWarp {
     for (int k = 1; k < SZ; ++k) v = (i == k) ? a[k] : v;
     return v;
   }
+  static __device__ __forceinline__ double sel(const WArray<double>& a, int i) { return a[i]; }
 
   // sqrt(sum / n); a zero (or NaN / inf) sum goes through the library routine. One copy (instruction-cache footprint).
   static __device__ __noinline__ double wrms_finish(double sum)
@@ -899,33 +947,46 @@ struct BdfWarp {
       const double A1 = 1.0 - alpha0_hat + alpha0;
       const double A2 = 1.0 + q_ * A1;
       const double tq2 = fabs(fdiv(A1, alpha0 * A2));
-      tq[2] = tq2;
-      tq[5] = fabs(fdiv(A2 * xistar_inv, lq * xi_inv));
+      const double tq5 = fabs(fdiv(A2 * xistar_inv, lq * xi_inv));
+      double tq1 = 0.0, tq3 = 0.0;
       if (qw1) {
         if (q_ > 1) {
           const double C = fdiv(xistar_inv, lq);
           const double A3 = alpha0 + inv_int(q_);
           const double A4 = alpha0_hat + xi_inv;
           const double Cpinv = fdiv(1.0 - A4 + A3, A3);
-          tq[1] = fabs(C * Cpinv);
+          tq1 = fabs(C * Cpinv);
         } else
-          tq[1] = 1.0;
+          tq1 = 1.0;
         hsum += tau[q_];
         xi_inv = fdiv(h_, hsum);
         const double A5 = alpha0 - inv_int(q_ + 1);
         const double A6 = alpha0_hat - xi_inv;
         const double Cppinv = fdiv(1.0 - A6 + A5, A2);
-        tq[3] = fabs(fdiv(Cppinv, xi_inv * (q_ + 2) * A5));
+        tq3 = fabs(fdiv(Cppinv, xi_inv * (q_ + 2) * A5));
       }
-      tq[4] = fdiv(cvc::CORTES, tq2);
+      const double rl1v = frcp(l[1]);
+      const double g = h_ * rl1v;
+      const bool first = (nst == 0);
+      const double gp = first ? g : double(gammap);
+      const double gr = first ? 1.0 : fdiv(g, gp);
+      // everything above is in registers: one group of stores, one pair of warp barriers
+      __syncwarp();
+      tq[2].put(tq2);
+      tq[5].put(tq5);
+      if (qw1) {
+        tq[1].put(tq1);
+        tq[3].put(tq3);
+      }
+      tq[4].put(fdiv(cvc::CORTES, tq2));
 #pragma unroll
-      for (int i = 0; i <= QM; i++) lc[i] = l[i];
-      rl1 = frcp(l[1]);
+      for (int i = 0; i <= QM; i++) lc[i].put(l[i]);
+      rl1.put(rl1v);
+      gamma.put(g);
+      if (first) gammap.put(g);
+      gamrat.put(gr);
+      __syncwarp();
     }
-    const double g = h_ * rl1;
-    gamma = g;
-    if (nst == 0) gammap = g;
-    gamrat = (nst > 0) ? fdiv(g, gammap) : 1.0;
   }
   __device__ __forceinline__ int nls(int nflag)
   {
@@ -995,12 +1056,21 @@ struct BdfWarp {
 
   __device__ __forceinline__ void complete_step()
   {
-    nst++;
+    {  // nst, tau[]: read, then one group of stores
+      const int q_ = q, nst1 = nst + 1;
+      const double h_ = h;
+      double told[QM + 2];
 #pragma unroll
-    for (int i = QM; i >= 2; i--)
-      if (i <= q) tau[i] = tau[i - 1];
-    if ((q == 1) && (nst > 1)) tau[2] = tau[1];
-    tau[1] = h;
+      for (int i = 1; i <= QM; i++) told[i] = tau[i];
+      __syncwarp();
+      nst.put(nst1);
+#pragma unroll
+      for (int i = QM; i >= 2; i--)
+        if (i <= q_) tau[i].put(told[i - 1]);
+      if ((q_ == 1) && (nst1 > 1)) tau[2].put(told[1]);
+      tau[1].put(h_);
+      __syncwarp();
+    }
 #pragma unroll
     for (int j = 0; j <= QM; j++) {
       if (j <= q) {
@@ -1019,54 +1089,60 @@ struct BdfWarp {
     }
   }
 
-  __device__ __forceinline__ void set_eta()
-  {
-    if ((eta > cvc::ETA_MIN_FX) && (eta < cvc::ETA_MAX_FX)) {
-      eta = 1.0;
-      hprime = h;
-    } else {
-      if (eta >= cvc::ETA_MAX_FX) eta = fmin(eta, etamax);
-      else eta = fmax(eta, cvc::ETA_MIN);
-      hprime = h * eta;
-    }
-  }
-
+  // cvPrepareNextStep + cvSetEta (+ the new etamax, which cvStep sets right after): every decision in registers, then ONE
+  // group of stores (eta, qprime, hprime, qwait, etamax) between one pair of warp barriers
   __device__ __forceinline__ void prepare_next_step(double dsm)
   {
-    if (etamax == 1.0) {
-      qwait = max(qwait, 2);
-      qprime = q;
-      hprime = h;
-      eta = 1.0;
-      return;
-    }
-    const double etaq = frcp(rroot(cvc::BIAS2 * dsm, L_) + cvc::ADDON);
-    if (qwait != 0) {
-      eta = etaq;
-      qprime = q;
+    const double h_ = h, etamax_ = etamax;
+    const int q_ = q;
+    int qwait_ = qwait, qprime_ = q_;
+    double eta_ = 1.0, hprime_ = h_;
+    if (etamax_ == 1.0) {
+      qwait_ = max(qwait_, 2);
     } else {
-      choose_order(etaq);
+      const double etaq = frcp(rroot(cvc::BIAS2 * dsm, L_) + cvc::ADDON);
+      if (qwait_ != 0) {
+        eta_ = etaq;
+      } else {
+        qwait_ = 2;
+        choose_order(etaq, eta_, qprime_);
+      }
+      // cvSetEta
+      if ((eta_ > cvc::ETA_MIN_FX) && (eta_ < cvc::ETA_MAX_FX)) {
+        eta_ = 1.0;
+      } else {
+        if (eta_ >= cvc::ETA_MAX_FX) eta_ = fmin(eta_, etamax_);
+        else eta_ = fmax(eta_, cvc::ETA_MIN);
+        hprime_ = h_ * eta_;
+      }
     }
-    set_eta();  // single call site (instruction-cache footprint)
+    const double etamax_new = (nst <= cvc::SMALL_NST) ? cvc::ETA_MAX_ES : cvc::ETA_MAX_GS;
+    __syncwarp();
+    eta.put(eta_);
+    qprime.put(qprime_);
+    hprime.put(hprime_);
+    qwait.put(qwait_);
+    etamax.put(etamax_new);
+    __syncwarp();
   }
 
-  // cvPrepareNextStep with qwait == 0: cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta
-  __device__ __forceinline__ void choose_order(const double etaq)
+  // cvPrepareNextStep with qwait == 0: cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta (no scalar is stored here)
+  __device__ __forceinline__ void choose_order(const double etaq, double& eta_out, int& qprime_out)
   {
-    qwait = 2;
+    const int q_ = q;
     double etaqm1 = 0.0, etaqp1 = 0.0;
-    if (q > 1) {
+    if (q_ > 1) {
       double a = 0.0;
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         if (valid(s)) {
-          const double p = wb[L::ZN + q * NP + lane + 32 * s] * ewt[s];
+          const double p = wb[L::ZN + q_ * NP + lane + 32 * s] * ewt[s];
           a += p * p;
         }
       const double ddn = wrms_finish(warp_sum(a)) * tq[1];
-      etaqm1 = frcp(rroot(cvc::BIAS1 * ddn, q) + cvc::ADDON);
+      etaqm1 = frcp(rroot(cvc::BIAS1 * ddn, q_) + cvc::ADDON);
     }
-    if (q != o.qmax && saved_tq5 != 0.0) {
+    if (q_ != o.qmax && saved_tq5 != 0.0) {
       const double cquot = fdiv(tq[5], saved_tq5) * rpowI(fdiv(h, tau[2]), L_);
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
@@ -1076,17 +1152,17 @@ struct BdfWarp {
     }
     const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
     if ((etam > cvc::ETA_MIN_FX) && (etam < cvc::ETA_MAX_FX)) {
-      eta = 1.0;
-      qprime = q;
+      eta_out = 1.0;
+      qprime_out = q_;
     } else if (etam == etaq) {
-      eta = etaq;
-      qprime = q;
+      eta_out = etaq;
+      qprime_out = q_;
     } else if (etam == etaqm1) {
-      eta = etaqm1;
-      qprime = q - 1;
+      eta_out = etaqm1;
+      qprime_out = q_ - 1;
     } else {
-      eta = etaqp1;
-      qprime = q + 1;
+      eta_out = etaqp1;
+      qprime_out = q_ + 1;
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         if (valid(s)) wb[L::ZN + o.qmax * NP + lane + 32 * s] = acor[s];
@@ -1114,8 +1190,7 @@ struct BdfWarp {
       break;
     }
     complete_step();
-    prepare_next_step(dsm);
-    etamax = (nst <= cvc::SMALL_NST) ? cvc::ETA_MAX_ES : cvc::ETA_MAX_GS;
+    prepare_next_step(dsm);   // also sets the new etamax
     const double t2 = tq[2];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acor[s] *= t2;

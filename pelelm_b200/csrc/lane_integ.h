@@ -94,7 +94,7 @@ struct LaneLay {
   static constexpr int SC = F + N;                    // table-driven kernels: concentrations [NS] and g/RT [NS] of the
   static constexpr int G = SC + NS;                   // right-hand side / Jacobian being evaluated
   static constexpr int SCAL = M::kTable ? G + NS : F + N;   // cvode's tau[QM+3], tq[6], l[QM+3]
-  static constexpr int FAST_BDF = SCAL + 2 * (QM + 3) + 6;
+  static constexpr int FAST_BDF = SCAL + (QM + 1) + 5 + (QM + 2);
   static constexpr int RK_F = 3 * N, RK_SC = RK_F + N, RK_G = RK_SC + NS;   // RK64: soln, carry, err, (f, sc, g)
   static constexpr int FAST_RK = M::kTable ? RK_G + NS : 3 * N;
   // ---- BIG space ----
@@ -237,6 +237,10 @@ constexpr int FIRST_CALL = 6, PREV_CONV_FAIL = 7, PREV_ERR_FAIL = 8;
 constexpr int CV_NO_FAILURES = 0, CV_FAIL_BAD_J = 1, CV_FAIL_OTHER = 2;
 }  // namespace cv
 
+#ifdef LANE_MODEL_COUNT_SWAPS
+static long lane_model_swaps = 0, lane_model_pivots = 0, lane_model_lus = 0, lane_model_lus_swapped = 0;
+#endif
+
 template <class M, int QM, int EINT>
 struct LaneBdf {
   using L = LaneLay<M, QM>;
@@ -249,7 +253,9 @@ struct LaneBdf {
   double tn, h, hprime, hscale, eta, etamax, tout, t0;
   // cvode's tau[], tq[], l[] live in the FAST space (SCAL): as member arrays they are indexed dynamically, i.e. local
   // memory, and with the SM's shared memory given to the vectors local memory is served by the L2
-  static constexpr int T_TAU = L::SCAL, T_TQ = L::SCAL + NT, T_L = L::SCAL + NT + 6;
+  // (tau[1 .. QM+1], tq[1 .. 5] and l[0 .. QM+1] are the entries ever touched: the bases are shifted so that tau[1] and tq[1]
+  // are the first doubles of their blocks)
+  static constexpr int T_TAU = L::SCAL - 1, T_TQ = T_TAU + (QM + 1), T_L = T_TQ + 5 + 1;
   double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5, saved_t, dsm;
   double hg, hub, hlb, hsign;  // cvHin
   double rhoe_init, rhoesrc, hin_load, t_eval;
@@ -321,9 +327,11 @@ struct LaneBdf {
     saved_tq5 = 0.0;
     crate = 1.0; delp = 0.0; jcur = 0; eta = 1.0; qprime = 1;
 #pragma unroll
-    for (int i = 0; i < NT; ++i) w.d(T_TAU + i) = w.d(T_L + i) = 0.0;
+    for (int i = 1; i <= QM + 1; ++i) w.d(T_TAU + i) = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) w.d(T_TQ + (i)) = 0.0;
+    for (int i = 0; i <= QM + 1; ++i) w.d(T_L + i) = 0.0;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) w.d(T_TQ + i) = 0.0;
 #pragma unroll(VU)
     for (int i = 0; i < N; ++i) zn(w, 0, i) = w.d(L::Y + i);
     if (!ewtset(w)) {  // CVode returns CV_ILL_INPUT before any work: the state is the input
@@ -750,6 +758,9 @@ struct LaneBdf {
     constexpr int COL = L::ACOR;
     const double c = -gamma;
     int ier = 0;
+#ifdef LANE_MODEL_COUNT_SWAPS
+    const long swaps0 = lane_model_swaps;
+#endif
     for (int j = 0; j < N; ++j) {
       // column j of I - gamma J with the row interchanges of the columns before it
 #pragma unroll
@@ -785,6 +796,10 @@ struct LaneBdf {
         }
       }
       w.g(L::PERM + j) = double(lp);
+#ifdef LANE_MODEL_COUNT_SWAPS
+      lane_model_swaps += (lp != j);
+      lane_model_pivots += 1;
+#endif
       if (w.d(COL + lp) == 0.0) {
         ier = j + 1;
         break;
@@ -806,6 +821,10 @@ struct LaneBdf {
         w.g(L::MAT + j * N + i) = (i > j) ? v * mult : v;
       }
     }
+#ifdef LANE_MODEL_COUNT_SWAPS
+    lane_model_lus += 1;
+    lane_model_lus_swapped += (lane_model_swaps != swaps0);
+#endif
 #pragma unroll
     for (int i = 0; i < N; ++i) w.d(COL + i) = 0.0;
     return ier;

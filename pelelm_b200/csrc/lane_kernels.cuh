@@ -29,10 +29,17 @@ template <class I, class LAY>
 struct LaneShape {
   static constexpr int FAST = I::kBdf ? LAY::FAST_BDF : LAY::FAST_RK;
   static constexpr int BIG = I::kBdf ? LAY::BIG_BDF : LAY::BIG_RK;
-  static constexpr int LUA = I::kBdf ? LAY::N * (LAY::N + 1) : 0;   // per warp: one cell's Newton matrix (cooperative LU)
+#ifdef PLM_LANE_COOP_BUILD   // the warp-cooperative LU (measured and rejected, see coop_getrf) needs one matrix of scratch per warp
+  static constexpr int LUA = I::kBdf ? LAY::N * (LAY::N + 1) : 0;
+#else
+  static constexpr int LUA = 0;
+#endif
   static constexpr int WARP_BYTES = (FAST * 32 + LUA) * 8;
   static constexpr int FIT = (227 * 1024 - 1024) / WARP_BYTES;
-  static constexpr int WARPS = FIT >= 8 ? 8 : FIT;
+  // 8 warps of 255 registers fill the register file; the explicit integrator of the smallest mechanism needs 144 registers
+  // and is bound by FP64 dependency latency (`wait` stalls), so it runs 12
+  static constexpr int MAXW = (!I::kBdf && LAY::N <= 12) ? 12 : 8;
+  static constexpr int WARPS = FIT >= MAXW ? MAXW : FIT;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int SMEM = WARPS * WARP_BYTES + kMaxN * 8;
   static_assert(WARPS >= 1, "the per-cell vectors of one warp do not fit in shared memory");
@@ -182,7 +189,11 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
   // theta bit 29 (development, PLM_LANE_COOP=1): factorisations warp-cooperative, one cell at a time, as soon as a lane asks,
   // instead of lane-parallel when enough lanes wait.  Measured on B200 (profiles/r02f_*): 19 % fewer instructions, but the
   // warps of a CTA then carry different numbers of factorisations per round and wait for each other: drm19 -12 %, LiDryer -25 %.
+#ifdef PLM_LANE_COOP_BUILD
   const bool coop = (theta >> 29) & 1;
+#else
+  const bool coop = false;
+#endif
   theta &= 0x1fffffff;
 
 #pragma unroll 1
@@ -256,6 +267,7 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
           if (!coop) it.setup_finish(it.getrf(w));
         }
       }
+#ifdef PLM_LANE_COOP_BUILD
       if (coop) {
         unsigned lum = __ballot_sync(0xffffffffu, it.phase == PH_WAIT_SETUP && !it.need_jac);
         int my_ier = 0;
@@ -268,6 +280,7 @@ __global__ void __launch_bounds__(LaneShape<I, LAY>::THREADS, 1)
         }
         if (it.phase == PH_WAIT_SETUP && !it.need_jac) it.setup_finish(my_ier);
       }
+#endif
       // ---- (D) Newton correction and the step logic behind it, (E) the shared tail ----
       if (it.phase == PH_SOLVE) it.solve(w);
       it.tail(w);

@@ -149,6 +149,13 @@ int react_mech(int integ, int rt, int qmax, const LaneOpts& o, int ncells, doubl
   else return -1;
 
 extern "C" {
+#ifdef LANE_MODEL_COUNT_SWAPS
+void lane_model_swap_stats(long* out)
+{
+  out[0] = plm::lane::lane_model_swaps; out[1] = plm::lane::lane_model_pivots; out[2] = plm::lane::lane_model_lus;
+  out[3] = plm::lane::lane_model_lus_swapped;
+}
+#endif
 int lane_model_rhs(const char* mech, int rt, double t, const double* y, double* ydot, double rhoe, double rhoesrc,
                    const double* rys)
 {

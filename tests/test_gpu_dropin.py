@@ -64,7 +64,13 @@ def test_flamesheet_run_through_the_adaptor(tmp_path, plm_lib):
     for name, integ in (("ref", "ReactorCvode"), ("b200", "ReactorCvodeB200")):
         r = subprocess.run([exe, "inputs.2d-regt", "max_step=3", "peleLM.chem_integrator=" + integ, "amr.plot_file=plt_" + name,
                             "amr.plot_int=3", "amr.check_int=-1"], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+        logdir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(logdir):  # the full run log travels back from the GPU box
+            with open(os.path.join(logdir, "flamesheet_%s.log" % name), "w") as f:
+                f.write(r.stdout + "\n--- stderr ---\n" + r.stderr + "\n--- files ---\n" + "\n".join(sorted(os.listdir(str(tmp_path)))))
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        assert os.path.exists(str(tmp_path / ("plt_%s00003" % name) / "Header")), \
+            "no plotfile after 3 steps:\n" + r.stdout[:3000] + "\n...\n" + r.stdout[-3000:] + r.stderr[-2000:]
         m = re.findall(r"PLM::advance_chemistry\(\)\s+\d+\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)\s+([0-9.]+)%", r.stdout)
         times[name] = float(m[-1][2]) if m else None   # inclusive table: max time over ranks
     na, la = _read_plt(str(tmp_path / "plt_ref00003"))
