@@ -81,11 +81,10 @@ __device__ __forceinline__ double rpowI(double base, int e)
 // predicates. The iteration matrix is an approximation to begin with (stale J, stale gamma); the converged Newton
 // solution does not depend on how W b is rounded.
 template <class L>
-__device__ __noinline__ int gjinv_warp()
+__device__ __noinline__ int gjinv_warp(double* A)
 {
   constexpr int NSLOT = L::NSLOT, n = L::N, ld = L::LD;
   double* wb = warp_base<L>();
-  double* A = wb + L::A;
   int* perm = reinterpret_cast<int*>(wb + L::PERM);
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -242,12 +241,11 @@ __device__ __forceinline__ void argmax_first(double& v, int& idx)
 // brought up to date with pivot k on their own (lane = column) before the swap and the scaling. Row k itself, which
 // every lane reads as the first pivot row during the sweep, gets its pivot-(k+1) update after the sweep.
 template <class L>
-__device__ __noinline__ int gjinv2_warp()
+__device__ __noinline__ int gjinv2_warp(double* A)
 {
   constexpr int n = L::N, ld = L::LD;
   static_assert(L::NSLOT == 2 && L::PAIRS && n % 2 == 0 && n > 32, "two rows per lane, even order");
   double* wb = warp_base<L>();
-  double* A = wb + L::A;
   int* perm = reinterpret_cast<int*>(wb + L::PERM);
   const int lane = threadIdx.x & 31;
   const int i0 = lane, i1 = lane + 32;
@@ -405,7 +403,7 @@ __device__ __noinline__ int gjinv2_warp()
 
 // x = W (P b): in wb[FB] = b (every lane its own components), out = x of the lane's components.
 template <class L>
-__device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::NSLOT])
+__device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::NSLOT], const double* __restrict__ Wt)
 {
   constexpr int NSLOT = L::NSLOT, n = L::N, ld = L::LD;
   const int* perm = reinterpret_cast<const int*>(wb + L::PERM);
@@ -417,7 +415,27 @@ __device__ __forceinline__ void solve_warp(double* wb, int lane, double (&x)[L::
   for (int s = 0; s < NSLOT; ++s) wb[L::YB + lane + 32 * s] = t[s];  // YB is free between right-hand-side calls
   __syncwarp();
   const double* pb = wb + L::YB;
-  if (NSLOT == 2 && L::PAIRS) {  // both rows of the lane against one pass over the right-hand side: four independent chains
+  if constexpr (L::POOL > 0) {
+    // W streamed from the warp's global buffer (L2), transposed: element (row, col) at Wt[col * WLD + row], so a column is
+    // one coalesced 256-byte load per slot. Same products, same order of accumulation as the shared-memory form below.
+    static_assert(NSLOT == 2 && n % 2 == 0, "pooled matrices: two rows per lane");
+    constexpr int wld = L::WLD;
+    const double2* pb2 = reinterpret_cast<const double2*>(pb);
+    const double* w0 = Wt + lane;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 9
+    for (int j = 0; j < n / 2; ++j) {
+      const double u0 = __ldcg(w0 + (2 * j) * wld), u1 = __ldcg(w0 + (2 * j + 1) * wld);
+      const double v0 = __ldcg(w0 + (2 * j) * wld + 32), v1 = __ldcg(w0 + (2 * j + 1) * wld + 32);
+      const double2 b = pb2[j];
+      a0 = fma(u0, b.x, a0);
+      a1 = fma(u1, b.y, a1);
+      b0 = fma(v0, b.x, b0);
+      b1 = fma(v1, b.y, b1);
+    }
+    x[0] = a0 + a1;
+    x[NSLOT - 1] = b0 + b1;
+  } else if (NSLOT == 2 && L::PAIRS) {  // both rows of the lane against one pass over the right-hand side: four independent chains
     const double2* r0 = reinterpret_cast<const double2*>(wb + L::A + lane * ld);
     const double2* r1 = reinterpret_cast<const double2*>(wb + L::A + min(lane + 32, n - 1) * ld);
     const double2* pb2 = reinterpret_cast<const double2*>(pb);
@@ -520,6 +538,7 @@ struct BdfWarp {
   const int lane;
   double* const wb;
   double* const Jsave;  // [n*ld] per-warp global scratch
+  double* const Wt;     // pooled matrices (Lay<>::POOL): [n][WLD] the transposed inverse of the last setup, behind Jsave
   const LaneVec atolv, ewt, acor;
   double yv[NSLOT], ft[NSLOT], dl[NSLOT], tv[NSLOT];  // short-lived temporaries
   const WArray<double> tau, lc, tq;
@@ -533,7 +552,7 @@ struct BdfWarp {
   __device__ __forceinline__ int* si() const { return reinterpret_cast<int*>(wb + L::SM + SC_I); }
   static __device__ __forceinline__ int* sip(double* w) { return reinterpret_cast<int*>(w + L::SM + SC_I); }
   __device__ BdfWarp(const BdfOpts& o_, int lane_, double* wb_, double* js)
-      : o(o_), lane(lane_), wb(wb_), Jsave(js),
+      : o(o_), lane(lane_), wb(wb_), Jsave(js), Wt(js + n * L::LD),
         atolv{wb_ + L::ATOL + lane_}, ewt{wb_ + L::EWT + lane_}, acor{wb_ + L::ACOR + lane_},
         tau{wb_ + L::SM + SC_TAU}, lc{wb_ + L::SM + SC_LC}, tq{wb_ + L::SM + SC_TQ},
         tn{wb_ + L::SM + SC_D + 0}, h{wb_ + L::SM + SC_D + 1}, hprime{wb_ + L::SM + SC_D + 2}, hscale{wb_ + L::SM + SC_D + 3},
@@ -648,7 +667,14 @@ struct BdfWarp {
   // cvNlsLSetup + cvLsSetup + cvLsLinSys + dense factorisation
   __device__ __forceinline__ int lsetup()
   {
-    double* A = wb + L::A;
+    int pool = 0;
+    double* A;
+    if constexpr (L::POOL > 0) {
+      pool = pool_acquire<L>();
+      A = pool_matrix<L>(pool);
+    } else {
+      A = wb + L::A;
+    }
     const double dgamma = fabs(fdiv(gamma, gammap) - 1.0);
     const bool jbad = (nst == 0) || (nst >= nstlj + o.msbj) ||
                       ((convfail == cvc::FAIL_BAD_J) && (dgamma < cvc::DGMAX_JBAD)) || (convfail == cvc::FAIL_OTHER);
@@ -686,11 +712,22 @@ struct BdfWarp {
     __syncwarp();
 #if !defined(PLM_GJ2) || PLM_GJ2
     int ier;
-    if constexpr (NSLOT == 2 && L::PAIRS) ier = gjinv2_warp<L>();
-    else ier = gjinv_warp<L>();
+    if constexpr (NSLOT == 2 && L::PAIRS) ier = gjinv2_warp<L>(A);
+    else ier = gjinv_warp<L>(A);
 #else
-    const int ier = gjinv_warp<L>();
+    const int ier = gjinv_warp<L>(A);
 #endif
+    if constexpr (L::POOL > 0) {
+      // W to the warp's global buffer, transposed (rows beyond n: zero), and the matrix back to the pool
+      for (int j = 0; j < n; ++j) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          const int i = lane + 32 * s;
+          __stcg(Wt + j * L::WLD + i, (i < n) ? A[i * ld + j] : 0.0);
+        }
+      }
+      pool_release<L>(pool);
+    }
     nsetups++;
     gamrat = 1.0;
     gammap = gamma;
@@ -741,7 +778,7 @@ struct BdfWarp {
         nni++;
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) wb[L::FB + lane + 32 * s] = -dl[s];
-        solve_warp<L>(wb, lane, dl);
+        solve_warp<L>(wb, lane, dl, Wt);
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) dl[s] = valid(s) ? dl[s] : 0.0;
         if (gamrat != 1.0) {

@@ -116,6 +116,9 @@ __device__ __forceinline__ double* block_prologue(const DevMech* __restrict__ dm
     stage(T::FO4, m.fo4, 32); stage(T::SEG, m.seg, (kMaxSeg * L::NP) / 2);
     stage(T::EFF, m.eff, m.emax * 64); stage(T::EFF + m.emax * 64, m.gat, m.glen * L::NP);
   }
+  if constexpr (L::POOL > 0) {
+    if (threadIdx.x < 32) reinterpret_cast<int*>(pool_base<L>() + L::POOL * L::MATD)[threadIdx.x] = 0;  // the locks: all free
+  }
   for (int sl = 0; sl < L::SLOTS; ++sl) {
     double* w = warp_slot<L>(sl);
     for (int e = lane; e < L::TOTAL; e += 32) w[e] = 0.0;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
   BdfOpts bo;
   bo.rtol = o.rtol; bo.atol = o.atol; bo.qmax = o.qmax; bo.maxcor = o.maxcor; bo.ajac = o.ajac;
   bo.mxstep = 10000; bo.maxnef = 100; bo.msbj = 100;
-  BdfWarp<L> bdf(bo, lane, wb, jglobal + size_t(gwarp) * n * L::LD);
+  BdfWarp<L> bdf(bo, lane, wb, jglobal + size_t(gwarp) * (n * L::LD + (L::POOL > 0 ? n * L::WLD : 0)));
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s) {
     const int i = lane + 32 * s;
@@ -653,13 +656,22 @@ __global__ void __launch_bounds__(L::WARPS * 32) jac_kernel(const DevMech* __res
     for (int s = 0; s < NSLOT; ++s)
       wb[L::YB + lane + 32 * s] = (lane + 32 * s < n) ? y[size_t(c) * n + lane + 32 * s] : 0.0;
     __syncwarp();
-    jac_warp<L>(wb + L::A);
+    int pool = 0;
+    double* A;
+    if constexpr (L::POOL > 0) {
+      pool = pool_acquire<L>();
+      A = pool_matrix<L>(pool);
+    } else {
+      A = wb + L::A;
+    }
+    jac_warp<L>(A);
     // column-major output like the SUNDenseMatrix handed to CVODE
     for (int e = lane; e < n * n; e += 32) {
       const int col = e / n, row = e - col * n;
-      Jout[size_t(c) * n * n + e] = wb[L::A + row * ld + col];
+      Jout[size_t(c) * n * n + e] = A[row * ld + col];
     }
     __syncwarp();
+    if constexpr (L::POOL > 0) pool_release<L>(pool);
   }
 }
 
@@ -820,7 +832,8 @@ static cudaError_t dispatch(const DevMech& m, int integ, int qmax, F&& f)
 template <class L>
 static size_t smem_bytes_of(const DevMech& m)
 {
-  return (size_t(kHdr) + size_t(L::WARPS) * L::SLOTS * L::TOTAL + size_t(Tab<L>::doubles(m.emax, m.glen))) * sizeof(double);
+  return (size_t(kHdr) + size_t(L::WARPS) * L::SLOTS * L::TOTAL + size_t(L::POOLD) + size_t(Tab<L>::doubles(m.emax, m.glen))) *
+         sizeof(double);
 }
 
 struct SmemQuery {
@@ -864,7 +877,7 @@ struct JQuery {
   template <class L, int IG>
   cudaError_t run()
   {
-    *out = size_t(L::N) * L::LD;
+    *out = size_t(L::N) * L::LD + (L::POOL > 0 ? size_t(L::N) * L::WLD : 0);  // saved Jacobian (+ the transposed inverse)
     return cudaSuccess;
   }
 };
