@@ -14,3 +14,23 @@ extern "C" void ref_knapsack(const long* wgts, int nboxes, int nprocs, int do_fu
     for (int id : result[b]) bucket_of_box[id] = b;
   if (efficiency) *efficiency = eff;
 }
+
+// BoxList::maxSize (amrex/Src/Base/AMReX_BoxList.cpp:774-827) on one cell-centred box: the pieces, in the reference's
+// order, as lo/hi triples. Returns the number of pieces (at most cap are written).
+#include <AMReX_BoxList.H>
+extern "C" int ref_max_size(const int* lo, const int* hi, const int* chunk, int* out_lohi, int cap)
+{
+  amrex::BoxList bl;
+  bl.push_back(amrex::Box(amrex::IntVect(AMREX_D_DECL(lo[0], lo[1], lo[2])), amrex::IntVect(AMREX_D_DECL(hi[0], hi[1], hi[2]))));
+  bl.maxSize(amrex::IntVect(AMREX_D_DECL(chunk[0], chunk[1], chunk[2])));
+  int n = 0;
+  for (const auto& b : bl) {
+    if (n < cap)
+      for (int d = 0; d < 3; ++d) {
+        out_lohi[6 * n + d] = d < AMREX_SPACEDIM ? b.smallEnd(d) : 0;
+        out_lohi[6 * n + 3 + d] = d < AMREX_SPACEDIM ? b.bigEnd(d) : 0;
+      }
+    ++n;
+  }
+  return n;
+}

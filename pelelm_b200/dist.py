@@ -20,20 +20,33 @@ from . import capi
 
 
 def max_size(boxes, chunk):
-    """BoxArray::maxSize(chunk): chop every box so that no side is longer than chunk[d] (near-equal pieces)."""
+    """BoxList::maxSize(chunk) (AMReX_BoxList.cpp:774-827): chop every box so that no side is longer than chunk[d].
+    The common power of two of the side and the chunk is kept as the blocking factor of the pieces (a 48-cell side chopped
+    at 32 gives 32 + 16, not 24 + 24), the longer pieces come first, and the pieces are emitted x fastest."""
     out = []
     for lo, hi in boxes:
         cuts = []
         for d in range(3):
             n = hi[d] - lo[d] + 1
             c = max(1, int(chunk[d]))
-            k = (n + c - 1) // c
-            base, rem = divmod(n, k)
-            edges, s = [], lo[d]
+            if n <= c:
+                cuts.append([(lo[d], hi[d])])
+                continue
+            ratio, bs, nlen = 1, c, n
+            while bs % 2 == 0 and nlen % 2 == 0:
+                ratio, bs, nlen = ratio * 2, bs // 2, nlen // 2
+            k = (nlen + bs - 1) // bs
+            sz = nlen // k
+            extra = nlen - sz * k
+            edges = []
             for i in range(k):
-                ln = base + (1 if i < rem else 0)
-                edges.append((s, s + ln - 1))
-                s += ln
+                if i < extra:
+                    a = i * (sz + 1) * ratio
+                    b = a + (sz + 1) * ratio - 1
+                else:
+                    a = (i * sz + extra) * ratio
+                    b = a + sz * ratio - 1
+                edges.append((lo[d] + a, lo[d] + b))
             cuts.append(edges)
         for kz in cuts[2]:
             for jy in cuts[1]:

@@ -295,6 +295,21 @@ def knap():
         out["w%d" % i], out["b%d" % i], out["e%d" % i], out["n%d" % i] = w, res, np.array(eff.value), np.array(nr)
     np.savez_compressed(os.path.join(HERE, "knapsack.npz"), **out)
     print("knapsack golden written")
+    # BoxList::maxSize pieces of single boxes (the chopping advance_chemistry applies before the knapsack, PeleLM.cpp:5660-5687)
+    R.L.ref_max_size.argtypes = [c_ip, c_ip, c_ip, c_ip, C.c_int]
+    R.L.ref_max_size.restype = C.c_int
+    mo = {}
+    mcases = [((0, 0, 0), (63, 127, 63), (32, 32, 32)), ((0, 0, 0), (47, 47, 47), (32, 32, 32)), ((4, -8, 16), (103, 39, 79), (32, 16, 64)),
+              ((0, 0, 0), (99, 0, 0), (32, 32, 32)), ((0, 0, 0), (95, 71, 23), (64, 64, 64)), ((0, 0, 0), (30, 44, 50), (16, 16, 16)),
+              ((0, 0, 0), (255, 255, 255), (128, 128, 64)), ((1, 1, 1), (90, 90, 90), (24, 40, 56))]
+    for i, (lo, hi, ch) in enumerate(mcases):
+        buf = np.zeros(6 * 4096, dtype=np.int32)
+        n = R.L.ref_max_size(np.array(lo, dtype=np.int32).ctypes.data_as(c_ip), np.array(hi, dtype=np.int32).ctypes.data_as(c_ip),
+                             np.array(ch, dtype=np.int32).ctypes.data_as(c_ip), buf.ctypes.data_as(c_ip), 4096)
+        assert 0 < n <= 4096
+        mo["lo%d" % i], mo["hi%d" % i], mo["chunk%d" % i], mo["pieces%d" % i] = np.array(lo), np.array(hi), np.array(ch), buf[:6 * n].reshape(n, 6)
+    np.savez_compressed(os.path.join(HERE, "maxsize.npz"), **mo)
+    print("maxSize golden written:", [mo["pieces%d" % i].shape[0] for i in range(len(mcases))])
 
 
 def vismf():

@@ -96,3 +96,19 @@ def test_chop_for_chemistry():
     # already enough boxes: untouched
     many = [((i * 16, 0, 0), (i * 16 + 15, 15, 15)) for i in range(40)]
     assert pd.chop_for_chemistry(many, (16, 16, 16), nranks=8, threshold=4) == many
+
+
+def test_max_size_vs_reference():
+    """dist.max_size against the pieces AMReX's own BoxList::maxSize produced (tests/golden/maxsize.npz, written by
+    make_golden.py through oracle/ref_knapsack.cpp::ref_max_size): same pieces, same order -- non-divisible sides, sides that
+    share a power of two with the chunk, boxes with a non-zero origin, directions that need no cut."""
+    from pelelm_b200 import dist as pd
+    g = np.load(os.path.join(ROOT, "tests", "golden", "maxsize.npz"))
+    i = 0
+    while "lo%d" % i in g:
+        lo, hi, ch = (tuple(int(v) for v in g[k + str(i)]) for k in ("lo", "hi", "chunk"))
+        got = pd.max_size([(lo, hi)], ch)
+        want = [(tuple(int(v) for v in r[:3]), tuple(int(v) for v in r[3:])) for r in g["pieces%d" % i]]
+        assert got == want, (i, lo, hi, ch)
+        i += 1
+    assert i == 8
