@@ -627,7 +627,14 @@ struct BdfWarp {
   {
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) wb[L::YB + lane + 32 * s] = y[s];
+#ifdef PLM_ALIGN
+    // Development experiment (profiles/r02n_*): the warps of the CTA enter every right-hand side
+    // together, so that they stream its code as one instruction stream.  Warps that ran out of cells keep arriving
+    // (react_kernel's epilogue) until every warp of the CTA has: all threads execute the same number of barriers.
+    __syncthreads_and(0);
+#else
     __syncwarp();
+#endif
     rhs_warp<L>(t);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) ydot[s] = wb[L::FB + lane + 32 * s];

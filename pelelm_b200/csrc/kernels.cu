@@ -370,6 +370,11 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
       }
     }
   }
+#ifdef PLM_ALIGN
+  // phase-aligned experiment: a warp that is out of cells keeps meeting the barrier of BdfWarp::f until all warps are out
+  if (INTEG == kIntegCvode)
+    while (!__syncthreads_and(1)) {}
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
