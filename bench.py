@@ -11,7 +11,9 @@ by the reference's cost-weighted knapsack on the previous pass's FC; NCCL carrie
 The same JSON line carries, under "also", the other configurations BASELINE.json names, measured in the same run with the
 same method on a bounded number of steps: dodecane_lu (configs[3]'s mechanism; 2^18 cells per GPU), LiDryer ReactorRK64
 (configs[1], 2^20 cells per GPU) and the 3-level TripleFlame AMR hierarchy at the survey's size (configs[4]; strong scaling,
-boxes re-dealt by the knapsack and moved between ranks over NCCL every pass).  --no-also skips them.
+boxes re-dealt by the knapsack and moved between ranks over NCCL every pass).  --no-also skips them.  At N = 8 one more
+entry, "dodecane_lu_256cubed", is configs[3] at its own size: 256^3 = 2^24 dodecane_lu cells over the 8 GPUs (one warm-up
+pass, one timed pass, ~3.5 min; PLM_BENCH_256CUBED=1 forces it at another N).
 
 A "step" = one react() pass over every box of the rank's shard, each step from the same pristine state (restored by a
 device-to-device copy inside the timed region).  value = cells advanced by dt per second, whole job, inputs resident in
@@ -354,7 +356,7 @@ def run_batch(a, ctx):
     def step():
         """One advance over the local shard + the cost / statistics reductions of advance_chemistry."""
         ids = sorted(boxes)
-        if not R.path_is_per_box():   # lane = cell kernels: every local box in ONE launch (plm_react_boxes)
+        if not R.path_is_per_box():   # every local box in ONE launch (plm_react_boxes): the queue's tail is paid once per step
             lst = []
             for b in ids:
                 bx = boxes[b]
@@ -628,6 +630,23 @@ def run_gpu_arm(a):
                 r = run_amr(sub, ctx) if name == "tripleflame" else run_batch(sub, ctx)
                 if r is not None:
                     also[name] = {k: r[k] for k in NESTED_KEYS if k in r}
+            # BASELINE.json configs[3] at its own size: 256^3 dodecane_lu cells over the GPUs of the box.  Two passes over 2^24
+            # cells cost ~3.5 min on 8 B200 and proportionally more on fewer, so the full domain runs where the config is
+            # named with the most GPUs (N = 8; PLM_BENCH_256CUBED=1 forces it at any N); the 2^18-cells-per-GPU entry above
+            # is the same kernel on the same states at every N.  A failure here must not cost the line.
+            if ctx["world"] == 8 or os.environ.get("PLM_BENCH_256CUBED") == "1":
+                sub = copy.copy(a)
+                sub.mech, sub.integrator = "dodecane_lu", "ReactorCvode"
+                sub.cells = int(os.environ.get("PLM_BENCH_256CUBED_CELLS", 256 ** 3)) // ctx["world"]
+                sub.steps, sub.warmup, sub.e2e_steps, sub.no_cpu_baseline = 1, 1, 0, True
+                try:
+                    r = run_batch(sub, ctx)
+                    if r is not None:
+                        also["dodecane_lu_256cubed"] = {k: r[k] for k in NESTED_KEYS if k in r}
+                        also["dodecane_lu_256cubed"]["scaling"] = "strong"
+                except Exception as e:  # noqa: BLE001
+                    if line is not None:
+                        also["dodecane_lu_256cubed"] = {"error": "%s: %s" % (type(e).__name__, e)}
             if line is not None:
                 line["also"] = also
     if line is not None:

@@ -85,7 +85,8 @@ int  plm_advance_chemistry_box(plm_reactor*, const int lo[3], const int hi[3], p
 /* Several boxes in ONE launch (device arrays only): react (mks = 0) or the fused advance_chemistry body (mks != 0, time = 0)
  * over every box of `boxes` -- the MFIter loop of PeleLM::advance_chemistry (PeleLM.cpp:5725-5780) for all local boxes of
  * a level at once.  The work queue then runs over the cells of all boxes, so its tail (the last, most expensive cells) is
- * paid once per level instead of once per box.  With the warp-per-cell kernels this is a loop of per-box launches.
+ * paid once per level instead of once per box (both kernel families; the environment variable PLM_BOXES_PER_LAUNCH=1
+ * keeps the warp-per-cell kernels on one launch per box, a development A/B).
  * The status array of plm_reactor_cell_status covers the boxes in the order given. */
 typedef struct plm_box {
   int lo[3], hi[3];

@@ -185,8 +185,12 @@ class Reactor:
         return self
 
     def path_is_per_box(self):
-        """True when a react_boxes call is a loop of per-box launches (warp-per-cell kernels), False when it is one launch"""
-        return not bool(self.L.plm_reactor_uses_lane(self.h))
+        """True when a react_boxes call is a loop of per-box launches, False when it is one launch over the cells of every box
+        (the default for both kernel families; PLM_BOXES_PER_LAUNCH=1 keeps the warp-per-cell kernels on one launch per box)"""
+        if bool(self.L.plm_reactor_uses_lane(self.h)):
+            return False
+        return os.environ.get("PLM_BOXES_PER_LAUNCH", "") == "1" or (
+            os.environ.get("PLM_RK64_DUAL", "") == "1" and self.integrator == "ReactorRK64")
 
     def set_path(self, path):
         """kernel family: 0 / "auto", 1 / "warp" (one warp per cell), 2 / "lane" (one thread per cell)"""

@@ -541,6 +541,9 @@ struct BdfWarp {
   double* const Wt;     // pooled matrices (Lay<>::POOL): [n][WLD] the transposed inverse of the last setup, behind Jsave
   const LaneVec atolv, ewt, acor;
   double yv[NSLOT], ft[NSLOT], dl[NSLOT], tv[NSLOT];  // short-lived temporaries
+#ifdef PLM_SOFTALIGN
+  bool in_setup = false;  // the warp is outside the soft barrier's group (difference-quotient Jacobian: f without arrival)
+#endif
   const WArray<double> tau, lc, tq;
   const WScalar<double> tn, h, hprime, hscale, eta, etamax;
   const WScalar<double> rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
@@ -632,6 +635,9 @@ struct BdfWarp {
     // together, so that they stream its code as one instruction stream.  Warps that ran out of cells keep arriving
     // (react_kernel's epilogue) until every warp of the CTA has: all threads execute the same number of barriers.
     __syncthreads_and(0);
+#elif defined(PLM_SOFTALIGN)
+    if (!in_setup) softbar_arrive_wait();  // (ends with a warp barrier)
+    else __syncwarp();
 #else
     __syncwarp();
 #endif
@@ -674,6 +680,17 @@ struct BdfWarp {
   // cvNlsLSetup + cvLsSetup + cvLsLinSys + dense factorisation
   __device__ __forceinline__ int lsetup()
   {
+#ifdef PLM_SOFTALIGN
+    softbar_leave();
+    in_setup = true;
+    const int ier_ = lsetup_body();
+    in_setup = false;
+    softbar_join();
+    return ier_;
+  }
+  __device__ __forceinline__ int lsetup_body()
+  {
+#endif
     int pool = 0;
     double* A;
     if constexpr (L::POOL > 0) {

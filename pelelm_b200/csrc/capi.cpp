@@ -281,7 +281,7 @@ int run_react(plm_reactor* r, plm::BoxArgs& a, cudaStream_t stream)
     a.FC.p = static_cast<double*>(sl.fcflat.p);
   }
   auto* ctrl = static_cast<unsigned long long*>(r->ctrl.p);
-  if (lane && a.nboxes > 0) {  // the boxes of a multi-box call: host vectors (a.tab / a.off) -> this slot's device table
+  if (a.nboxes > 0) {  // the boxes of a multi-box call: host vectors (a.tab / a.off) -> this slot's device table
     const size_t tb = size_t(a.nboxes) * sizeof(plm::BoxArgs), ob = size_t(a.nboxes + 1) * sizeof(int64_t);
     if (sl.boxtab.ensure(tb + ob) != 0) return fail(PLM_ERR_CUDA, "cudaMalloc failed");
     PLM_CUDA(cudaMemcpyAsync(sl.boxtab.p, a.tab, tb, cudaMemcpyHostToDevice, stream));
@@ -474,7 +474,12 @@ int plm_react_boxes(plm_reactor* r, int nboxes, const plm_box* boxes, double dt,
   const double t0 = mks ? 0.0 : time;  // PeleLM.cpp:5751
   for (int b = 0; b < nboxes; ++b)
     if (!is_device_ptr(boxes[b].rY.p)) return fail(PLM_ERR_ARG, "plm_react_boxes takes device arrays");
-  if (!use_lane(r)) {  // warp-per-cell kernels: one launch per box (they overlap on the caller's streams as before)
+  // One launch over the cells of every box (both kernel families: the work queue runs over all of them, so its tail is paid
+  // once per call).  PLM_BOXES_PER_LAUNCH=1 (development A/B) and the two-cells-per-warp ReactorRK64 experiment keep the
+  // warp-per-cell kernels on one launch per box.
+  static const bool per_box_env = [] { const char* e = std::getenv("PLM_BOXES_PER_LAUNCH"); return e && e[0] == '1'; }();
+  static const bool rk_dual_env = [] { const char* e = std::getenv("PLM_RK64_DUAL"); return e && e[0] == '1'; }();
+  if (!use_lane(r) && (per_box_env || (rk_dual_env && r->integ == plm::kIntegRK64))) {
     for (int b = 0; b < nboxes; ++b) {
       const plm_box& x = boxes[b];
       const int rc = react_box_impl(r, x.lo, x.hi, x.rY, x.rYsrc, x.T, x.rEner, x.rEner_src, x.FC, x.mask, &dt, &t0, cuda_stream,

@@ -100,6 +100,9 @@ __device__ __forceinline__ double* block_prologue(const DevMech* __restrict__ dm
   }
   const int lane = threadIdx.x & 31;
   if (lane == 0) *slot_word() = 0;
+#ifdef PLM_SOFTALIGN
+  if (threadIdx.x == 0) *softbar_word() = unsigned(blockDim.x >> 5);  // every warp a member, nobody arrived, generation 0
+#endif
   if constexpr (L::TSM) {  // stage the tables of the right-hand side behind the warp areas (once per CTA)
     __syncthreads();
     const DevMech& m = smem_mech();
@@ -138,12 +141,28 @@ __device__ __forceinline__ int64_t a4_off(const plm_a4d& a, int i, int j, int k)
 struct CellAddr {
   int64_t oY, oS, oT, oE, oEs, oF, oI, sY, sS;
   int mk;
+  int box;  // index into the box table of a multi-box call (plm_react_boxes), -1: the call's own box
 };
+// the box of a multi-box call that holds cell c (off[b] <= c < off[b + 1]); c becomes the cell's index inside it
+__device__ __forceinline__ int find_box(const BoxArgs& a0, int64_t& c)
+{
+  if (a0.nboxes <= 0) return -1;
+  int lo = 0, hi = a0.nboxes;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a0.off + mid) <= c) lo = mid;
+    else hi = mid;
+  }
+  c -= __ldg(a0.off + lo);
+  return lo;
+}
 template <class L>
-__device__ __noinline__ CellAddr cell_addr(const BoxArgs& a, int64_t c)
+__device__ __noinline__ CellAddr cell_addr(const BoxArgs& a0, int64_t c)
 {
   constexpr int ns = L::NS, n = L::N;
   CellAddr r;
+  r.box = find_box(a0, c);
+  const BoxArgs& a = (r.box >= 0) ? a0.tab[r.box] : a0;
   r.mk = 1;
   if (a.flat) {
     r.oY = c * n; r.oS = c * ns; r.oT = c * n + ns; r.oE = c; r.oEs = c; r.oF = c; r.oI = 0; r.sY = 1; r.sS = 1;
@@ -165,7 +184,7 @@ __device__ __noinline__ CellAddr cell_addr(const BoxArgs& a, int64_t c)
 
 template <class L, int INTEG>
 __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
-    react_kernel(const DevMech* __restrict__ dm, const ReactOpts o, const BoxArgs a, unsigned long long* __restrict__ counter,
+    react_kernel(const DevMech* __restrict__ dm, const ReactOpts o, const __grid_constant__ BoxArgs a, unsigned long long* __restrict__ counter,
                  unsigned long long* __restrict__ gstats, int* __restrict__ status, double* __restrict__ jglobal)
 {
   constexpr int NSLOT = L::NSLOT, ns = L::NS, n = L::N;
@@ -208,9 +227,11 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
       const int64_t c = int64_t(c0) + cc;
       if (c >= ncells) break;
       CellAddr ad = cell_addr<L>(a, c);
+      // the arrays of the cell's box: the call's own, or an entry of the box table of a multi-box call (plm_react_boxes)
+      const BoxArgs* bxp = (ad.box >= 0) ? a.tab + ad.box : &a;
       if (INTEG == kIntegCvode && ad.mk == -1) {  // ReactorCvode.cpp:1395, :1439-1441 (RK64 ignores the mask)
         if (lane == 0) {
-          a.FC.p[ad.oF] = 0.0;
+          bxp->FC.p[ad.oF] = 0.0;
           if (status) status[c] = 0;
           atomicAdd(gstats + 8, 1ull);
         }
@@ -219,24 +240,24 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
           for (int s = 0; s < NSLOT; ++s) {
             const int k = lane + 32 * s;
             if (k < ns) {
-              double* dst = a.rY.p + ad.oY + int64_t(k) * ad.sY;
+              double* dst = bxp->rY.p + ad.oY + int64_t(k) * ad.sY;
               const double vold = *dst, vnew = __dmul_rn(__dmul_rn(vold, 1.0e-3), 1.0e3);
-              if (a.IR.p)
-                a.IR.p[ad.oI + int64_t(k) * a.IR.nstride] =
-                    __dsub_rn(__dmul_rn(-__dsub_rn(vold, vnew), a.dt_inv), a.rYsrc.p[ad.oS + int64_t(k) * ad.sS]);
+              if (bxp->IR.p)
+                bxp->IR.p[ad.oI + int64_t(k) * bxp->IR.nstride] =
+                    __dsub_rn(__dmul_rn(-__dsub_rn(vold, vnew), a.dt_inv), bxp->rYsrc.p[ad.oS + int64_t(k) * ad.sS]);
               *dst = vnew;
             }
           }
-          if (lane == 0) a.rE.p[ad.oE] = __dmul_rn(__dmul_rn(a.rE.p[ad.oE], 10.0), 0.1);
+          if (lane == 0) bxp->rE.p[ad.oE] = __dmul_rn(__dmul_rn(bxp->rE.p[ad.oE], 10.0), 0.1);
         }
         continue;
       }
       double y[NSLOT];
-      const double Tin = a.T.p[ad.oT];
+      const double Tin = bxp->T.p[ad.oT];
       const bool mks = a.mks != 0;
       // __dmul_rn / __dadd_rn: the scalings are separate, rounded operations in the reference (no contraction into FMAs)
-      const double rhoe_init = mks ? __dmul_rn(a.rE.p[ad.oE], 10.0) : a.rE.p[ad.oE];
-      const double rhoesrc = mks ? __dmul_rn(a.rEsrc.p[ad.oEs], 10.0) : a.rEsrc.p[ad.oEs];
+      const double rhoe_init = mks ? __dmul_rn(bxp->rE.p[ad.oE], 10.0) : bxp->rE.p[ad.oE];
+      const double rhoesrc = mks ? __dmul_rn(bxp->rEsrc.p[ad.oEs], 10.0) : bxp->rEsrc.p[ad.oEs];
       __syncwarp();
       const bool clean = (INTEG == kIntegCvode) && o.clean_init_massfrac && !a.flat;
       double rho_old = 0.0;
@@ -245,8 +266,8 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
           const int k = lane + 32 * s;
-          ry0[s] = (k < ns) ? a.rY.p[ad.oY + int64_t(k) * ad.sY] : 0.0;
-          double sv = (k < ns) ? a.rYsrc.p[ad.oS + int64_t(k) * ad.sS] : 0.0;
+          ry0[s] = (k < ns) ? bxp->rY.p[ad.oY + int64_t(k) * ad.sY] : 0.0;
+          double sv = (k < ns) ? bxp->rYsrc.p[ad.oS + int64_t(k) * ad.sS] : 0.0;
           if (mks) {  // PeleLM.cpp:5737-5746
             ry0[s] = __dmul_rn(ry0[s], 1.0e-3);
             sv = __dmul_rn(sv, 1.0e-3);
@@ -305,6 +326,7 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
       }
       // box_unflatten (addresses recomputed: nothing of the cell's bookkeeping stays live across the integration)
       ad = cell_addr<L>(a, c);
+      bxp = (ad.box >= 0) ? a.tab + ad.box : &a;
       const double rhoe0 = wb[L::SM + 24], rhoesrc0 = wb[L::SM + 25];
       double outv[NSLOT], p2 = 0.0;
 #pragma unroll
@@ -312,7 +334,7 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
         const int k = lane + 32 * s;
         outv[s] = y[s];
         if (clean) {  // ReactorUtils.H:160-166: the loaded and the clipped state, recomputed from the value still in the FAB
-          double r0 = (k < ns) ? a.rY.p[ad.oY + int64_t(k) * ad.sY] : 0.0;
+          double r0 = (k < ns) ? bxp->rY.p[ad.oY + int64_t(k) * ad.sY] : 0.0;
           if (mks) r0 = __dmul_rn(r0, 1.0e-3);
           const double cl = (k < ns) ? fmin(fmax(0.0, r0), wb[L::SM + 56]) : 0.0;
           outv[s] = r0 + (y[s] - cl) * wb[L::SM + 56] / wb[L::SM + 57];
@@ -337,13 +359,13 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
       for (int s = 0; s < NSLOT; ++s) {
         const int k = lane + 32 * s;
         if (k < ns) {
-          double* dst = a.rY.p + ad.oY + int64_t(k) * ad.sY;
+          double* dst = bxp->rY.p + ad.oY + int64_t(k) * ad.sY;
           if (mks) {  // CGS -> MKS (PeleLM.cpp:5765-5772), then I_R (PeleLM.cpp:5795-5799) from the old value still in place
             const double vnew = __dmul_rn(outv[s], 1.0e3);
-            if (a.IR.p) {
+            if (bxp->IR.p) {
               const double vold = *dst;
-              const double frc = a.rYsrc.p[ad.oS + int64_t(k) * ad.sS];
-              a.IR.p[ad.oI + int64_t(k) * a.IR.nstride] = __dsub_rn(__dmul_rn(-__dsub_rn(vold, vnew), a.dt_inv), frc);
+              const double frc = bxp->rYsrc.p[ad.oS + int64_t(k) * ad.sS];
+              bxp->IR.p[ad.oI + int64_t(k) * bxp->IR.nstride] = __dsub_rn(__dmul_rn(-__dsub_rn(vold, vnew), a.dt_inv), frc);
             }
             *dst = vnew;
           } else {
@@ -352,9 +374,9 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
         }
       }
       if (lane == 0) {
-        a.T.p[ad.oT] = Tout;
-        a.rE.p[ad.oE] = mks ? __dmul_rn(rE_new, 0.1) : rE_new;
-        a.FC.p[ad.oF] = double(fc);
+        bxp->T.p[ad.oT] = Tout;
+        bxp->rE.p[ad.oE] = mks ? __dmul_rn(rE_new, 0.1) : rE_new;
+        bxp->FC.p[ad.oF] = double(fc);
         if (status) status[c] = st.flag;
         atomicAdd(gstats + 0, (unsigned long long)st.nst);
         atomicAdd(gstats + 1, (unsigned long long)st.nfe);
@@ -374,6 +396,8 @@ __global__ void __launch_bounds__(L::WARPS * 32, L::MINB)
   // phase-aligned experiment: a warp that is out of cells keeps meeting the barrier of BdfWarp::f until all warps are out
   if (INTEG == kIntegCvode)
     while (!__syncthreads_and(1)) {}
+#elif defined(PLM_SOFTALIGN)
+  if (INTEG == kIntegCvode) softbar_leave();  // out of cells: the others stop waiting for this warp
 #endif
 }
 
