@@ -6,7 +6,7 @@
  * reference (oracle/_ref, built by oracle/Makefile) in tests/test_oracle_port_vs_ref.py, and
  * against committed fixtures generated from it (tests/golden/) where /root/reference is absent.
  *
- * The mechanism is table driven (oracle/port/gen/tables_<mech>.c) instead of generated straight-line
+ * The mechanism is table driven (pelelm_b200/csrc/gen/tables_<mech>.c: DATA shared with the product) instead of generated straight-line
  * code; evaluation order per reaction follows the reference's generated kernels so results agree to
  * rounding. Reference locations cited are for drm19 (Support/Mechanism/Models/drm19/mechanism.H);
  * LiDryer and dodecane_lu have the same functions at other lines.

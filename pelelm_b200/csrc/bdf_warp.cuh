@@ -713,17 +713,19 @@ struct BdfWarp {
       } else {
         dq_jac(A);
       }
-      // large mechanisms: streaming stores / loads, the small L1 left beside 190 KB of shared memory stays with the
-      // mechanism tables (dodecane_lu +5 %); small ones keep the saved Jacobian L1 resident (drm19 -4 % if streamed)
+      // large mechanisms: L2-only stores / loads (.cg) -- the small L1 left beside 190 KB of shared memory stays with the
+      // mechanism tables (dodecane_lu +5 % against L1-cached accesses) and the 23 KB per warp stay in L2 instead of being
+      // written through to HBM as the streaming (.cs) form of round 1 did (55-84 KB of DRAM traffic per cell against 1.3 KB
+      // of state; same speed); small ones keep the saved Jacobian L1 resident (drm19 -4 % if it bypasses L1)
       for (int e = lane; e < n * ld; e += 32) {
-        if (L::BIG) __stcs(Jsave + e, A[e]);
+        if (L::BIG) __stcg(Jsave + e, A[e]);
         else Jsave[e] = A[e];
       }
       nje++;
       nstlj = nst;
     } else {
       jcur = 0;
-      for (int e = lane; e < n * ld; e += 32) A[e] = L::BIG ? __ldcs(Jsave + e) : Jsave[e];
+      for (int e = lane; e < n * ld; e += 32) A[e] = L::BIG ? __ldcg(Jsave + e) : Jsave[e];
     }
     __syncwarp();
     const double c = -gamma;
