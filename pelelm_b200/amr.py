@@ -6,8 +6,9 @@ What the reference does per level (PeleLM::advance_chemistry, Source/PeleLM.cpp:
   1. `dm = getFuncCountDM(ba, ngrow)` (:5529-5623, :5689): per-box cost = sum of the previous pass's FC, gathered on every
      rank, knapsack -> chemistry owner of every box (all-zero FC keeps the state's own map);
   2. `STemp / FTemp.ParallelCopy` (:5692-5696): state and forcing of every box travel to its chemistry owner;
-  3. the MFIter loop (:5725-5775): MKS->CGS, react, CGS->MKS per box -- here ONE fused launch per box
-     (`plm_advance_chemistry_box`), which also forms I_R = (new - old)/dt - F (:5789-5803);
+  3. the MFIter loop (:5725-5775): MKS->CGS, react, CGS->MKS per box -- here ONE fused launch over every local box of the
+     level (`plm_react_boxes`; `plm_advance_chemistry_box` per box when `multi=False`), which also forms
+     I_R = (new - old)/dt - F (:5789-5803);
   4. `mf_new / FC.ParallelCopy` back to the state's map (:5780, :5812);
   5. `average_down(fine_React, React_new)` (:5818-5822) when `avg_down_chem` and a finer level with old I_R exists: the I_R
      of covered coarse cells is replaced by the average of the fine level's previous I_R.
@@ -263,9 +264,10 @@ def advance_hierarchy(levels, dt, advance_box, **kw):
 
 
 def gpu_advance(reactor, streams=None, multi=True):
-    """(advance_box, wait) for advance_chemistry_level on the GPU: one fused `plm_advance_chemistry_box` launch per box
-    (device arrays, the box as its own FAB), launches spread round robin over `streams`; wait() drains them and returns
-    the integrator statistics accumulated since the previous wait()."""
+    """(advance_box, wait) for advance_chemistry_level on the GPU: one fused launch over every local box of the level
+    (`multi`, `plm_react_boxes`), or one `plm_advance_chemistry_box` launch per box spread round robin over `streams`
+    (device arrays, the box as its own FAB); wait() drains them and returns the integrator statistics accumulated since
+    the previous wait()."""
     ns = reactor.ns
     launches = [0]
 

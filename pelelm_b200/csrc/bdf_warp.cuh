@@ -519,6 +519,21 @@ struct WScalar {
     return old;
   }
 };
+// A statistics counter (right-hand sides, Newton iterations, Jacobians, setups, failures): nothing in the integration reads
+// it, so lane 0 keeps it alone -- plain increments, no barrier -- and every lane reads it once, behind a warp barrier, when
+// the cell is done.  (As WScalar these six cost two warp barriers per increment: four per right-hand side.)
+struct WCount {
+  int* p;
+  __device__ __forceinline__ void operator++(int) const
+  {
+    if ((threadIdx.x & 31) == 0) *p = *p + 1;
+  }
+  __device__ __forceinline__ void reset() const
+  {
+    if ((threadIdx.x & 31) == 0) *p = 0;
+  }
+  __device__ __forceinline__ int final_value() const { return *p; }  // after a __syncwarp()
+};
 template <class T>
 struct WArray {
   T* p;
@@ -548,7 +563,8 @@ struct BdfWarp {
   const WScalar<double> tn, h, hprime, hscale, eta, etamax;
   const WScalar<double> rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
   const WScalar<int> q, qprime, L_, qwait, indx_acor;
-  const WScalar<int> nst, nfe, ncfn, netf, nni, nsetups, nje, nstlp, nstlj;
+  const WScalar<int> nst, nstlp, nstlj;
+  const WCount nfe, ncfn, netf, nni, nsetups, nje;
   const WScalar<int> jcur, convfail;
 
   __device__ __forceinline__ double* sc() const { return wb + L::SM; }
@@ -961,10 +977,13 @@ struct BdfWarp {
       }
     }
   }
-  __device__ __forceinline__ void predict()
+  // cvPredict: the new tn is handed to set_bdf, which stores it with its own group of scalars (one pair of warp barriers
+  // for both; nothing reads tn in between)
+  __device__ __forceinline__ double predict()
   {
-    tn += h;
+    const double tn_new = tn + h;
     pascal<1>();
+    return tn_new;
   }
   __device__ __forceinline__ void restore(double saved_t)
   {
@@ -973,7 +992,7 @@ struct BdfWarp {
   }
   // cvSetBDF + cvSetTqBDF (coefficients formed in registers, stored once). Reusing the previous step's values when
   // (q, h, tau, qwait == 1) are unchanged was tried and measured slower (the key compare costs more than it saves).
-  __device__ __forceinline__ void set_bdf()
+  __device__ __forceinline__ void set_bdf(double tn_new)
   {
     const int q_ = q;
     const double h_ = h;
@@ -1048,19 +1067,24 @@ struct BdfWarp {
       gamma.put(g);
       if (first) gammap.put(g);
       gamrat.put(gr);
+      tn.put(tn_new);
       __syncwarp();
     }
   }
   __device__ __forceinline__ int nls(int nflag)
   {
-    convfail = ((nflag == cvc::FIRST_CALL) || (nflag == cvc::PREV_ERR_FAIL)) ? cvc::NO_FAILURES : cvc::FAIL_OTHER;
+    // cv_jcur = SUNFALSE belongs behind a successful solve (cvode_nls.c); it is only ever read right after a setup has set
+    // it, so clearing it here, in one store group with convfail, is the same thing and one pair of warp barriers less
+    __syncwarp();
+    convfail.put(((nflag == cvc::FIRST_CALL) || (nflag == cvc::PREV_ERR_FAIL)) ? cvc::NO_FAILURES : cvc::FAIL_OTHER);
+    jcur.put(0);
+    __syncwarp();
     const bool callSetup = (nflag == cvc::PREV_CONV_FAIL) || (nflag == cvc::PREV_ERR_FAIL) || (nst == 0) ||
                            (nst >= nstlp + cvc::MSBP) || (fabs(gamrat - 1.0) > cvc::DGMAX_LSETUP);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acor[s] = 0.0;
     const int flag = newton(callSetup);
     if (flag != cvc::NLS_SUCCESS) return flag;
-    jcur = 0;
     return 0;
   }
 
@@ -1120,13 +1144,14 @@ struct BdfWarp {
   __device__ __forceinline__ void complete_step()
   {
     {  // nst, tau[]: read, then one group of stores
-      const int q_ = q, nst1 = nst + 1;
+      const int q_ = q, nst1 = nst + 1, qwait1 = qwait - 1;
       const double h_ = h;
       double told[QM + 2];
 #pragma unroll
       for (int i = 1; i <= QM; i++) told[i] = tau[i];
       __syncwarp();
       nst.put(nst1);
+      qwait.put(qwait1);
 #pragma unroll
       for (int i = QM; i >= 2; i--)
         if (i <= q_) tau[i].put(told[i - 1]);
@@ -1142,7 +1167,6 @@ struct BdfWarp {
           if (valid(s)) zn(j, s) = lc[j] * acor[s] + zn(j, s);
       }
     }
-    qwait--;
     if ((qwait == 1) && (q != o.qmax)) {
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
@@ -1241,8 +1265,7 @@ struct BdfWarp {
     nflag = cvc::FIRST_CALL;
 #pragma unroll 1
     for (;;) {
-      predict();
-      set_bdf();
+      set_bdf(predict());
       nflag = nls(nflag);
       kflag = handle_nflag(nflag, saved_t, ncf);
       if (kflag == cvc::PREDICT_AGAIN) continue;
@@ -1322,7 +1345,8 @@ struct BdfWarp {
     L_ = 2;
     qwait = L_;
     etamax = cvc::ETA_MAX_FS;
-    nst = nfe = ncfn = netf = nni = nsetups = nje = nstlp = nstlj = 0;
+    nst = nstlp = nstlj = 0;
+    nfe.reset(); ncfn.reset(); netf.reset(); nni.reset(); nsetups.reset(); nje.reset();
     saved_tq5 = 0.0;
     indx_acor = o.qmax;
     crate = 1.0;
@@ -1411,13 +1435,14 @@ struct BdfWarp {
       for (int s = 0; s < NSLOT; ++s)
         if (valid(s)) yio[s] = zn(0, s);
     }
+    __syncwarp();  // lane 0's counters
     st.nst = nst;
-    st.nfe = nfe;
-    st.nje = nje;
-    st.nsetups = nsetups;
-    st.nni = nni;
-    st.ncfn = ncfn;
-    st.netf = netf;
+    st.nfe = nfe.final_value();
+    st.nje = nje.final_value();
+    st.nsetups = nsetups.final_value();
+    st.nni = nni.final_value();
+    st.ncfn = ncfn.final_value();
+    st.netf = netf.final_value();
     st.flag = istate;
     return istate;
   }
