@@ -730,9 +730,9 @@ struct BdfWarp {
         dq_jac(A);
       }
       // large mechanisms: L2-only stores / loads (.cg) -- the small L1 left beside 190 KB of shared memory stays with the
-      // mechanism tables (dodecane_lu +5 % against L1-cached accesses) and the 23 KB per warp stay in L2 instead of being
-      // written through to HBM as the streaming (.cs) form of round 1 did (55-84 KB of DRAM traffic per cell against 1.3 KB
-      // of state; same speed); small ones keep the saved Jacobian L1 resident (drm19 -4 % if it bypasses L1)
+      // mechanism tables (dodecane_lu +5 % against L1-cached accesses) and the 23 KB per warp stay L2 resident (2.1 KB of
+      // DRAM traffic per cell against 1.3 KB of state, profiles/r02r_dram_modes.txt; the streaming .cs form of round 1
+      // measures the same speed); small ones keep the saved Jacobian L1 resident (drm19 -4 % if it bypasses L1)
       for (int e = lane; e < n * ld; e += 32) {
         if (L::BIG) __stcg(Jsave + e, A[e]);
         else Jsave[e] = A[e];
@@ -1141,60 +1141,51 @@ struct BdfWarp {
     return cvc::TRY_AGAIN;
   }
 
-  __device__ __forceinline__ void complete_step()
+  // cvCompleteStep + cvPrepareNextStep + cvSetEta (+ the new etamax, which cvStep sets right after).  Every new scalar is
+  // formed in registers -- the later decisions read the NEW nst / qwait from those registers, as the reference reads them
+  // from memory -- and everything is stored in ONE group between one pair of warp barriers.  Measured one change at a time
+  // (profiles/r02v_groups_ab.txt, drm19 2^18 cells): this merge 244.0 k -> 247.3 k cells*dt/s; moving convfail / jcur into
+  // set_bdf's group 247.2 k, acnrm in a register 246.2 k, rescale / setup-tail groups 243.7 k -- but all four together
+  // 235.7 k: at this point the kernel answers to code layout (its per-step code is 34-37 KB against a 32 KB instruction
+  // cache), not to the barrier count, so only this one is in.
+  __device__ __forceinline__ void complete_and_prepare(double dsm)
   {
-    {  // nst, tau[]: read, then one group of stores
-      const int q_ = q, nst1 = nst + 1, qwait1 = qwait - 1;
-      const double h_ = h;
-      double told[QM + 2];
+    const int q_ = q, nst1 = nst + 1, qwait1 = qwait - 1, L0 = L_;
+    const double h_ = h, etamax_ = etamax;
+    double told[QM + 2];
 #pragma unroll
-      for (int i = 1; i <= QM; i++) told[i] = tau[i];
-      __syncwarp();
-      nst.put(nst1);
-      qwait.put(qwait1);
-#pragma unroll
-      for (int i = QM; i >= 2; i--)
-        if (i <= q_) tau[i].put(told[i - 1]);
-      if ((q_ == 1) && (nst1 > 1)) tau[2].put(told[1]);
-      tau[1].put(h_);
-      __syncwarp();
-    }
+    for (int i = 1; i <= QM; i++) told[i] = tau[i];
+    // cvCompleteStep: zn += l * acor; the correction kept for a possible order increase
 #pragma unroll
     for (int j = 0; j <= QM; j++) {
-      if (j <= q) {
+      if (j <= q_) {
+        const double lj = lc[j];
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
-          if (valid(s)) zn(j, s) = lc[j] * acor[s] + zn(j, s);
+          if (valid(s)) zn(j, s) = lj * acor[s] + zn(j, s);
       }
     }
-    if ((qwait == 1) && (q != o.qmax)) {
+    const bool keep = (qwait1 == 1) && (q_ != o.qmax);
+    const double tq5_ = tq[5];
+    if (keep) {
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         if (valid(s)) wb[L::ZN + o.qmax * NP + lane + 32 * s] = acor[s];
-      saved_tq5 = tq[5];
-      indx_acor = o.qmax;
     }
-  }
-
-  // cvPrepareNextStep + cvSetEta (+ the new etamax, which cvStep sets right after): every decision in registers, then ONE
-  // group of stores (eta, qprime, hprime, qwait, etamax) between one pair of warp barriers
-  __device__ __forceinline__ void prepare_next_step(double dsm)
-  {
-    const double h_ = h, etamax_ = etamax;
-    const int q_ = q;
-    int qwait_ = qwait, qprime_ = q_;
+    // cvPrepareNextStep / cvSetEta
+    int qwait_ = qwait1, qprime_ = q_;
     double eta_ = 1.0, hprime_ = h_;
     if (etamax_ == 1.0) {
       qwait_ = max(qwait_, 2);
     } else {
-      const double etaq = frcp(rroot(cvc::BIAS2 * dsm, L_) + cvc::ADDON);
+      const double etaq = frcp(rroot(cvc::BIAS2 * dsm, L0) + cvc::ADDON);
       if (qwait_ != 0) {
         eta_ = etaq;
       } else {
         qwait_ = 2;
-        choose_order(etaq, eta_, qprime_);
+        // choose_order reads tau[2], saved_tq5 as they are after cvCompleteStep: the shifted tau[2] is told[1] (or h for q == 1)
+        choose_order(etaq, eta_, qprime_, (q_ >= 2) ? told[1] : ((nst1 > 1) ? told[1] : tau[2]), keep ? tq5_ : double(saved_tq5));
       }
-      // cvSetEta
       if ((eta_ > cvc::ETA_MIN_FX) && (eta_ < cvc::ETA_MAX_FX)) {
         eta_ = 1.0;
       } else {
@@ -1203,8 +1194,18 @@ struct BdfWarp {
         hprime_ = h_ * eta_;
       }
     }
-    const double etamax_new = (nst <= cvc::SMALL_NST) ? cvc::ETA_MAX_ES : cvc::ETA_MAX_GS;
+    const double etamax_new = (nst1 <= cvc::SMALL_NST) ? cvc::ETA_MAX_ES : cvc::ETA_MAX_GS;
     __syncwarp();
+    nst.put(nst1);
+#pragma unroll
+    for (int i = QM; i >= 2; i--)
+      if (i <= q_) tau[i].put(told[i - 1]);
+    if ((q_ == 1) && (nst1 > 1)) tau[2].put(told[1]);
+    tau[1].put(h_);
+    if (keep) {
+      saved_tq5.put(tq5_);
+      indx_acor.put(o.qmax);
+    }
     eta.put(eta_);
     qprime.put(qprime_);
     hprime.put(hprime_);
@@ -1214,7 +1215,9 @@ struct BdfWarp {
   }
 
   // cvPrepareNextStep with qwait == 0: cvComputeEtaqm1 / cvComputeEtaqp1 / cvChooseEta (no scalar is stored here)
-  __device__ __forceinline__ void choose_order(const double etaq, double& eta_out, int& qprime_out)
+  // (tau2 / stq5: tau[2] and saved_tq5 as cvCompleteStep leaves them -- the caller has not stored them yet)
+  __device__ __forceinline__ void choose_order(const double etaq, double& eta_out, int& qprime_out, const double tau2,
+                                               const double stq5)
   {
     const int q_ = q;
     double etaqm1 = 0.0, etaqp1 = 0.0;
@@ -1229,8 +1232,8 @@ struct BdfWarp {
       const double ddn = wrms_finish(warp_sum(a)) * tq[1];
       etaqm1 = frcp(rroot(cvc::BIAS1 * ddn, q_) + cvc::ADDON);
     }
-    if (q_ != o.qmax && saved_tq5 != 0.0) {
-      const double cquot = fdiv(tq[5], saved_tq5) * rpowI(fdiv(h, tau[2]), L_);
+    if (q_ != o.qmax && stq5 != 0.0) {
+      const double cquot = fdiv(tq[5], stq5) * rpowI(fdiv(h, tau2), L_);
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         tv[s] = valid(s) ? -cquot * wb[L::ZN + o.qmax * NP + lane + 32 * s] + acor[s] : 0.0;
@@ -1275,8 +1278,7 @@ struct BdfWarp {
       if (eflag != 0) return eflag;
       break;
     }
-    complete_step();
-    prepare_next_step(dsm);   // also sets the new etamax
+    complete_and_prepare(dsm);
     const double t2 = tq[2];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) acor[s] *= t2;
