@@ -561,7 +561,8 @@ struct BdfWarp {
 #endif
   const WArray<double> tau, lc, tq;
   const WScalar<double> tn, h, hprime, hscale, eta, etamax;
-  const WScalar<double> rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
+  const WScalar<double> rl1, gamma, gammap, gamrat, crate, delp, saved_tq5;
+  double acnrm = 0.0;  // norm of the accepted correction: from the end of the Newton iteration to the error test, a register
   const WScalar<int> q, qprime, L_, qwait, indx_acor;
   const WScalar<int> nst, nstlp, nstlj;
   const WCount nfe, ncfn, netf, nni, nsetups, nje;
@@ -577,7 +578,7 @@ struct BdfWarp {
         tn{wb_ + L::SM + SC_D + 0}, h{wb_ + L::SM + SC_D + 1}, hprime{wb_ + L::SM + SC_D + 2}, hscale{wb_ + L::SM + SC_D + 3},
         eta{wb_ + L::SM + SC_D + 4}, etamax{wb_ + L::SM + SC_D + 5}, rl1{wb_ + L::SM + SC_D + 6}, gamma{wb_ + L::SM + SC_D + 7},
         gammap{wb_ + L::SM + SC_D + 8}, gamrat{wb_ + L::SM + SC_D + 9}, crate{wb_ + L::SM + SC_D + 10},
-        delp{wb_ + L::SM + SC_D + 11}, acnrm{wb_ + L::SM + SC_D + 12}, saved_tq5{wb_ + L::SM + SC_D + 13},
+        delp{wb_ + L::SM + SC_D + 11}, saved_tq5{wb_ + L::SM + SC_D + 13},
         q{sip(wb_) + 0}, qprime{sip(wb_) + 1}, L_{sip(wb_) + 2}, qwait{sip(wb_) + 3}, indx_acor{sip(wb_) + 4}, nst{sip(wb_) + 5},
         nfe{sip(wb_) + 6}, ncfn{sip(wb_) + 7}, netf{sip(wb_) + 8}, nni{sip(wb_) + 9}, nsetups{sip(wb_) + 10}, nje{sip(wb_) + 11},
         nstlp{sip(wb_) + 12}, nstlj{sip(wb_) + 13}, jcur{sip(wb_) + 14}, convfail{sip(wb_) + 15}
@@ -1147,7 +1148,8 @@ struct BdfWarp {
   // (profiles/r02v_groups_ab.txt, drm19 2^18 cells): this merge 244.0 k -> 247.3 k cells*dt/s; moving convfail / jcur into
   // set_bdf's group 247.2 k, acnrm in a register 246.2 k, rescale / setup-tail groups 243.7 k -- but all four together
   // 235.7 k: at this point the kernel answers to code layout (its per-step code is 34-37 KB against a 32 KB instruction
-  // cache), not to the barrier count, so only this one is in.
+  // cache), not to the barrier count.  On top of this merge (profiles/r02y_groups_ab2.txt): acnrm in
+  // a register 249.9 k, convfail / jcur in set_bdf's group 245.7 k, both 246.3 k -- so this one and acnrm are in.
   __device__ __forceinline__ void complete_and_prepare(double dsm)
   {
     const int q_ = q, nst1 = nst + 1, qwait1 = qwait - 1, L0 = L_;
