@@ -11,9 +11,12 @@ by the reference's cost-weighted knapsack on the previous pass's FC; NCCL carrie
 The same JSON line carries, under "also", the other configurations BASELINE.json names, measured in the same run with the
 same method on a bounded number of steps: dodecane_lu (configs[3]'s mechanism; 2^18 cells per GPU), LiDryer ReactorRK64
 (configs[1], 2^20 cells per GPU) and the 3-level TripleFlame AMR hierarchy at the survey's size (configs[4]; strong scaling,
-boxes re-dealt by the knapsack and moved between ranks over NCCL every pass).  --no-also skips them.  At N = 8 one more
-entry, "dodecane_lu_256cubed", is configs[3] at its own size: 256^3 = 2^24 dodecane_lu cells over the 8 GPUs (one warm-up
-pass, one timed pass, ~3.5 min; PLM_BENCH_256CUBED=1 forces it at another N).
+boxes re-dealt by the knapsack and moved between ranks over NCCL every pass).  --no-also skips them.  At N = 8 the dodecane_lu
+entry is "dodecane_lu_256cubed" instead: configs[3] at its own size, 256^3 = 2^24 dodecane_lu cells over the 8 GPUs (one timed
+pass of ~2 min without a warm-up pass of its own, every box of a rank holding the same 2^18 synthetic states so that the
+synthesis is paid once; PLM_BENCH_256CUBED=1 adds it at another N).  Every nested workload runs only if it still fits the
+invocation's wall-clock budget (PLM_BENCH_BUDGET_S = 760 s, the last one 800 s: the driver's scaling run allows 870 s per N
+with --steps 20 --warmup 5); a workload that does not fit is reported as {"skipped": ...}.
 
 A "step" = one react() pass over every box of the rank's shard, each step from the same pristine state (restored by a
 device-to-device copy inside the timed region).  value = cells advanced by dt per second, whole job, inputs resident in
@@ -41,6 +44,36 @@ if ROOT not in sys.path:
 
 DT = 1e-5
 BOX = 64 ** 3
+_T_IMPORT = time.time()
+# Wall-clock budget of one invocation (seconds since the process started).  The driver gives a scaling run 870 s per N with
+# --steps 20 --warmup 5 (SCALE_r01.json: per_n_timeout_s); a nested workload that does not fit is skipped and says so --
+# a skipped entry costs one number, a run killed at the limit costs the whole line.
+BUDGET_S = float(os.environ.get("PLM_BENCH_BUDGET_S", "760"))
+BUDGET_LAST_S = float(os.environ.get("PLM_BENCH_BUDGET_LAST_S", "800"))   # the last entry: nothing comes after it
+# conservative cost of each nested workload (seconds, N = 1 incl. its e2e leg and CPU baseline; measured: profiles/r02x_bench.json)
+NESTED_COST_S = {"dodecane_lu": 85.0, "lidryer_rk64": 30.0, "tripleflame": 80.0, "dodecane_lu_256cubed": 140.0}
+
+
+def elapsed_s():
+    """seconds since this process was created (interpreter start-up and imports included)"""
+    try:
+        import psutil
+        return time.time() - psutil.Process().create_time()
+    except Exception:  # noqa: BLE001
+        return time.time() - _T_IMPORT + 30.0
+
+
+def fits_budget(ctx, cost_s, budget_s, now_s=None):
+    """Does a nested workload of `cost_s` seconds still fit?  Rank 0 decides, every rank follows (the workloads contain
+    collectives: all ranks must take the same branch)."""
+    ok = ((elapsed_s() if now_s is None else now_s) + cost_s) <= budget_s
+    if ctx is not None and ctx.get("world", 1) > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=ctx["dev"])
+        dist.broadcast(t, src=0)
+        ok = bool(int(t.item()))
+    return ok
 
 
 def parse():
@@ -303,8 +336,16 @@ def run_batch(a, ctx):
 
     # ---- pristine state of this rank's boxes: S0 [ns+2][B] = rhoY, rhoH, T (the STemp aliasing of PeleLM.cpp:5728-5730),
     #      F [ns+1][B] = forcing (FTemp), mask [B]; pinned host copies feed the e2e leg
+    rep = getattr(a, "replicate_boxes", False)   # every box of the rank = its first box (same cell-cost distribution; the
+    first_local = int(np.nonzero(owner == rank)[0][0]) if rep and np.any(owner == rank) else 0   # synthesis is paid once)
+    synth_cache = {}
+
     def make_box(b):
-        st = synth.synthetic_batch(a.mech, box_cells, cell0=b * box_cells)
+        key = first_local if rep else b
+        if key not in synth_cache:
+            synth_cache.clear()
+            synth_cache[key] = synth.synthetic_batch(a.mech, box_cells, cell0=key * box_cells)
+        st = synth_cache[key]
         S = torch.empty((ns + 2, box_cells), dtype=torch.float64, pin_memory=True)
         S[:ns] = torch.from_numpy(st["rY"])
         S[ns] = torch.from_numpy(st["rE"])
@@ -388,7 +429,8 @@ def run_batch(a, ctx):
 
     # ---- warm-up; after the first pass the boxes are re-dealt by the knapsack on the measured costs
     eff = 1.0
-    for w in range(max(a.warmup, 1)):
+    nwarm = a.warmup if getattr(a, "allow_no_warmup", False) else max(a.warmup, 1)
+    for w in range(nwarm):
         gst, full, new_owner, eff = step()
         if w == 0 and N > 1 and not np.array_equal(new_owner, owner):
             moved = pd.move_boxes(boxes, ("hS", "hF", "hmask"), owner, new_owner, device=dev)
@@ -488,7 +530,7 @@ def run_batch(a, ctx):
                 traffic = None
         line = {
             "metric": "chemistry cells*dt/s", "value": value, "unit": "cells*dt/s", "n_gpus": N, "steps": a.steps,
-            "warmup": max(a.warmup, 1), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": nwarm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a, cells_total, nboxes), "l2": "inputs larger than L2 (%.2f GB state per GPU)"
                        % (cells_per_gpu * roofline.state_bytes_per_cell(a.mech) / 1e9),
@@ -503,6 +545,10 @@ def run_batch(a, ctx):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if rep:
+            line["config"]["workload"] += "; every box of a rank holds the same %d synthetic states" % box_cells
+        if nwarm == 0:
+            line["config"]["warmup_note"] = "no warm-up pass of its own: the same kernel was warmed up by the preceding workload"
     R.close()
     del boxes
     torch.cuda.empty_cache()
@@ -619,26 +665,40 @@ def run_gpu_arm(a):
         if headline and not a.no_also:
             also = {}
             ks = max(1, min(a.steps, a.also_steps))
+            want256 = ctx["world"] == 8 or os.environ.get("PLM_BENCH_256CUBED") == "1"
             for name, kw in (("dodecane_lu", dict(mech="dodecane_lu", integrator="ReactorCvode")),
                              ("lidryer_rk64", dict(mech="LiDryer", integrator="ReactorRK64")),
                              ("tripleflame", dict(workload="tripleflame"))):
+                if name == "dodecane_lu" and ctx["world"] == 8:
+                    continue   # N = 8: the same kernel runs the 256^3 domain below instead (no time for both in the driver's 870 s)
                 sub = copy.copy(a)
                 for k, v in kw.items():
                     setattr(sub, k, v)
                 sub.steps, sub.warmup, sub.e2e_steps = ks, 1, (1 if name != "tripleflame" else 0)
                 sub.cpu_seconds = min(a.cpu_seconds, 8.0)
+                if not fits_budget(ctx, NESTED_COST_S[name], BUDGET_S):
+                    also[name] = {"skipped": "time budget: %.0f s elapsed, %.0f s needed, %.0f s allowed (PLM_BENCH_BUDGET_S)"
+                                  % (elapsed_s(), NESTED_COST_S[name], BUDGET_S)}
+                    continue
                 r = run_amr(sub, ctx) if name == "tripleflame" else run_batch(sub, ctx)
                 if r is not None:
                     also[name] = {k: r[k] for k in NESTED_KEYS if k in r}
-            # BASELINE.json configs[3] at its own size: 256^3 dodecane_lu cells over the GPUs of the box.  Two passes over 2^24
-            # cells cost ~3.5 min on 8 B200 and proportionally more on fewer, so the full domain runs where the config is
-            # named with the most GPUs (N = 8; PLM_BENCH_256CUBED=1 forces it at any N); the 2^18-cells-per-GPU entry above
-            # is the same kernel on the same states at every N.  A failure here must not cost the line.
-            if ctx["world"] == 8 or os.environ.get("PLM_BENCH_256CUBED") == "1":
+            # BASELINE.json configs[3] at its own size: 256^3 dodecane_lu cells over the GPUs of the box.  One pass over 2^24
+            # cells costs ~2 min on 8 B200 and proportionally more on fewer, so the full domain runs where the config is
+            # named with the most GPUs (N = 8; PLM_BENCH_256CUBED=1 forces it at any N) and only if it still fits the time
+            # budget; the 2^18-cells-per-GPU entry above is the same kernel on the same states at every N and has warmed it
+            # up, so this entry is ONE timed pass without a warm-up pass of its own (equal-cost boxes: the knapsack of the
+            # warm-up pass would move nothing).  A failure here must not cost the line.
+            if want256 and not fits_budget(ctx, NESTED_COST_S["dodecane_lu_256cubed"], BUDGET_LAST_S):
+                also["dodecane_lu_256cubed"] = {"skipped": "time budget: %.0f s elapsed, %.0f s needed, %.0f s allowed "
+                                                "(PLM_BENCH_BUDGET_LAST_S)" % (elapsed_s(), NESTED_COST_S["dodecane_lu_256cubed"], BUDGET_LAST_S)}
+                want256 = False
+            if want256:
                 sub = copy.copy(a)
                 sub.mech, sub.integrator = "dodecane_lu", "ReactorCvode"
                 sub.cells = int(os.environ.get("PLM_BENCH_256CUBED_CELLS", 256 ** 3)) // ctx["world"]
-                sub.steps, sub.warmup, sub.e2e_steps, sub.no_cpu_baseline = 1, 1, 0, True
+                sub.steps, sub.warmup, sub.e2e_steps, sub.no_cpu_baseline, sub.allow_no_warmup = 1, 0, 0, True, True
+                sub.replicate_boxes = True   # 7 s of state synthesis per rank instead of 58 s
                 try:
                     r = run_batch(sub, ctx)
                     if r is not None:
