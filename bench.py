@@ -15,7 +15,7 @@ boxes re-dealt by the knapsack and moved between ranks over NCCL every pass).  -
 entry is "dodecane_lu_256cubed" instead: configs[3] at its own size, 256^3 = 2^24 dodecane_lu cells over the 8 GPUs (one timed
 pass of ~2 min without a warm-up pass of its own, every box of a rank holding the same 2^18 synthetic states so that the
 synthesis is paid once; PLM_BENCH_256CUBED=1 adds it at another N).  Every nested workload runs only if it still fits the
-invocation's wall-clock budget (PLM_BENCH_BUDGET_S = 760 s, the last one 800 s: the driver's scaling run allows 870 s per N
+invocation's wall-clock budget (PLM_BENCH_BUDGET_S = 790 s, the last one 800 s: the driver's scaling run allows 870 s per N
 with --steps 20 --warmup 5); a workload that does not fit is reported as {"skipped": ...}.
 
 A "step" = one react() pass over every box of the rank's shard, each step from the same pristine state (restored by a
@@ -48,10 +48,11 @@ _T_IMPORT = time.time()
 # Wall-clock budget of one invocation (seconds since the process started).  The driver gives a scaling run 870 s per N with
 # --steps 20 --warmup 5 (SCALE_r01.json: per_n_timeout_s); a nested workload that does not fit is skipped and says so --
 # a skipped entry costs one number, a run killed at the limit costs the whole line.
-BUDGET_S = float(os.environ.get("PLM_BENCH_BUDGET_S", "760"))
+BUDGET_S = float(os.environ.get("PLM_BENCH_BUDGET_S", "790"))
 BUDGET_LAST_S = float(os.environ.get("PLM_BENCH_BUDGET_LAST_S", "800"))   # the last entry: nothing comes after it
-# conservative cost of each nested workload (seconds, N = 1 incl. its e2e leg and CPU baseline; measured: profiles/r02x_bench.json)
-NESTED_COST_S = {"dodecane_lu": 85.0, "lidryer_rk64": 30.0, "tripleflame": 80.0, "dodecane_lu_256cubed": 140.0}
+# cost of each nested workload (seconds, N = 1 incl. state synthesis, its e2e leg and CPU baseline, padded by ~20 %; the three
+# of the default run took 138 s together in profiles/r02x_bench.json: ~70 + ~15 + ~53; the 256^3 pass is 115 s + 7 s of synthesis)
+NESTED_COST_S = {"dodecane_lu": 80.0, "lidryer_rk64": 25.0, "tripleflame": 65.0, "dodecane_lu_256cubed": 140.0}
 
 
 def elapsed_s():

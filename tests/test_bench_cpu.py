@@ -28,10 +28,13 @@ def test_budget_single_rank():
     assert not bench.fits_budget(None, 100.0, 760.0, now_s=700.0)
     assert bench.fits_budget({"world": 1}, 135.0, 800.0, now_s=665.0)
     # the driver's scaling run: 870 s per N; the budgets leave room for the process to wind down
-    assert bench.BUDGET_S < bench.BUDGET_LAST_S < 870.0
+    assert bench.BUDGET_S <= bench.BUDGET_LAST_S < 870.0 - 60.0
     # every nested workload has a cost estimate, and all of them together fit behind a 20 + 5 step headline (~560 s)
     assert set(bench.NESTED_COST_S) == {"dodecane_lu", "lidryer_rk64", "tripleflame", "dodecane_lu_256cubed"}
-    assert 560.0 + sum(v for k, v in bench.NESTED_COST_S.items() if k != "dodecane_lu_256cubed") <= bench.BUDGET_S
+    assert 600.0 + sum(v for k, v in bench.NESTED_COST_S.items() if k != "dodecane_lu_256cubed") <= bench.BUDGET_S
+    # N = 8: no small dodecane entry, no CPU baselines (~575 s headline), then the 256^3 pass
+    assert 575.0 + bench.NESTED_COST_S["lidryer_rk64"] + bench.NESTED_COST_S["tripleflame"] + bench.NESTED_COST_S["dodecane_lu_256cubed"] \
+        <= bench.BUDGET_LAST_S + 10.0
 
 
 def _worker(rank, ws, port, q):
