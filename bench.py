@@ -57,11 +57,15 @@ NESTED_COST_S = {"dodecane_lu": 80.0, "lidryer_rk64": 25.0, "tripleflame": 65.0,
 
 def elapsed_s():
     """seconds since this process was created (interpreter start-up and imports included)"""
+    since_import = time.time() - _T_IMPORT
     try:
         import psutil
-        return time.time() - psutil.Process().create_time()
+        e = time.time() - psutil.Process().create_time()
+        if since_import <= e <= since_import + 600.0:   # a clock the container reports consistently
+            return e
     except Exception:  # noqa: BLE001
-        return time.time() - _T_IMPORT + 30.0
+        pass
+    return since_import + 30.0
 
 
 def fits_budget(ctx, cost_s, budget_s, now_s=None):
