@@ -34,7 +34,7 @@ struct BoxArgs {
   int mks;
   plm_a4d IR;      // N components, p == nullptr: not wanted
   double dt_inv;   // 1/dt as the host computes it (PeleLM.cpp:5792)
-  // several boxes in one launch (lane = cell kernels; plm_react_boxes): nboxes > 0 => cell c of the call is cell
+  // several boxes in one launch (both kernel families; plm_react_boxes): nboxes > 0 => cell c of the call is cell
   // c - off[b] of tab[b], off[b] <= c < off[b + 1]; lo / hi / arrays / mask come from tab[b], everything else from this struct
   const BoxArgs* tab;
   const int64_t* off;
