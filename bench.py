@@ -529,7 +529,9 @@ def run_batch(a, ctx):
             try:
                 ent = json.load(open(tp)).get(a.mech if a.integrator == "ReactorCvode" else a.mech + "_rk64", {})
                 dram_per_cell = ent.get("dram_bytes_per_cell")
-                traffic = dram_per_cell * box_cells if dram_per_cell else None  # one launch = one box
+                # one launch = every local box of the rank (plm_react_boxes), or one box (PLM_BOXES_PER_LAUNCH=1)
+                launch_cells = box_cells if R.path_is_per_box() else cells_per_gpu
+                traffic = dram_per_cell * launch_cells if dram_per_cell else None
                 traffic_src = ent.get("source")
             except Exception:
                 traffic = None
