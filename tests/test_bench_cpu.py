@@ -65,3 +65,58 @@ def test_budget_decision_is_rank_zeros():
         p.join(60)
         assert p.exitcode == 0
     assert out == [(0, True, False), (1, True, False)]
+
+
+def _fake_line(a, ctx):
+    return {"metric": "chemistry cells*dt/s", "value": 1.0, "unit": "cells*dt/s", "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1.0,
+            "scaling": "weak", "config": {"workload": "%s %s %s" % (a.mech, a.integrator, a.cells)}, "roofline": {}, "e2e": None,
+            "gpu_launches": 1}
+
+
+def _run_arm(monkeypatch, capsys, world, elapsed, fail=()):
+    import json
+    import bench
+    calls = []
+
+    def fake_batch(a, ctx):
+        calls.append(("batch", a.mech, a.integrator, a.cells, a.steps, a.warmup, getattr(a, "allow_no_warmup", False),
+                      getattr(a, "replicate_boxes", False)))
+        if a.mech in fail:
+            raise RuntimeError("boom")
+        return _fake_line(a, ctx)
+
+    def fake_amr(a, ctx):
+        calls.append(("amr",))
+        return _fake_line(a, ctx)
+
+    monkeypatch.setattr(bench, "gpu_context", lambda: {"rank": 0, "world": world, "local": 0, "dev": torch.device("cpu")})
+    monkeypatch.setattr(bench, "run_batch", fake_batch)
+    monkeypatch.setattr(bench, "run_amr", fake_amr)
+    monkeypatch.setattr(bench, "elapsed_s", lambda: elapsed)
+    # (the broadcast of the decision is covered by test_budget_decision_is_rank_zeros: here only the arithmetic)
+    monkeypatch.setattr(bench, "fits_budget", lambda ctx, cost, budget, now_s=None: (elapsed + cost) <= budget)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda: None)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", str(world), "--steps", "20", "--warmup", "5"])
+    bench.run_gpu_arm(bench.parse())
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 1   # ONE JSON line
+    return json.loads(out[0]), calls
+
+
+def test_nested_workloads_control_flow(monkeypatch, capsys):
+    """The `also` object of the bench line without a GPU: which nested workloads run at which N, with which settings, what a
+    time budget that is used up or a failing workload leaves behind -- and that exactly one JSON line is printed."""
+    line, calls = _run_arm(monkeypatch, capsys, world=1, elapsed=100.0)
+    assert sorted(line["also"]) == ["dodecane_lu", "lidryer_rk64", "tripleflame"]
+    assert ("batch", "dodecane_lu", "ReactorCvode", 0, 2, 1, False, False) in calls and ("amr",) in calls
+    # N = 8: the 256^3 domain takes the place of the small dodecane_lu entry -- one pass, no warm-up, replicated boxes
+    line, calls = _run_arm(monkeypatch, capsys, world=8, elapsed=100.0)
+    assert sorted(line["also"]) == ["dodecane_lu_256cubed", "lidryer_rk64", "tripleflame"]
+    assert ("batch", "dodecane_lu", "ReactorCvode", 256 ** 3 // 8, 1, 0, True, True) in calls
+    assert line["also"]["dodecane_lu_256cubed"]["scaling"] == "strong"
+    # out of time: every nested workload says so, the headline line is still printed
+    line, calls = _run_arm(monkeypatch, capsys, world=8, elapsed=795.0)
+    assert all("skipped" in v for v in line["also"].values()) and len(calls) == 1
+    # a nested workload that raises leaves an error entry, the others and the headline survive
+    line, calls = _run_arm(monkeypatch, capsys, world=2, elapsed=100.0, fail=("dodecane_lu",))
+    assert "error" in line["also"]["dodecane_lu"] and "value" in line["also"]["tripleflame"] and line["value"] == 1.0
