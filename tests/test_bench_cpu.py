@@ -120,3 +120,19 @@ def test_nested_workloads_control_flow(monkeypatch, capsys):
     # a nested workload that raises leaves an error entry, the others and the headline survive
     line, calls = _run_arm(monkeypatch, capsys, world=2, elapsed=100.0, fail=("dodecane_lu",))
     assert "error" in line["also"]["dodecane_lu"] and "value" in line["also"]["tripleflame"] and line["value"] == 1.0
+
+
+def test_flop_model_matches_survey_8d():
+    """pelelm_b200/roofline.py against the constants and formulas SURVEY.md section 8(d) states: F_lu = 2/3 n^3, F_solve = 2 n^2,
+    F_step = 40 n, the RK64 step = 6 F_rhs + 36 n, the state bytes per cell (2N+3)*8 + 4 + (N+3)*8 = 268 / 556 / 1324 (the
+    survey's own 284 for LiDryer does not follow from its formula; 556 and 1324 do), and the worked drm19 example."""
+    from pelelm_b200 import roofline as rf
+    for mech, ns in (("LiDryer", 9), ("drm19", 21), ("dodecane_lu", 53)):
+        n = ns + 1
+        f_rhs, f_jac, f_lu, f_solve, f_step, f_rk = rf.FLOPS[mech]
+        assert abs(f_lu - 2.0 / 3.0 * n ** 3) <= 1.0 and f_solve == 2 * n * n and f_step == 40 * n and f_rk == 6 * f_rhs + 36 * n
+    assert [rf.state_bytes_per_cell(m) for m in ("LiDryer", "drm19", "dodecane_lu")] == [268, 556, 1324]
+    # SURVEY 8(d): drm19 at nst = 200, n_rhs = 230, n_lu = 23, n_jac = 2, n_solve = 230 is "about 1.2 MFLOP per cell"
+    st = {"nst": 200, "nfe": 230, "nsetups": 23, "nje": 2, "nni": 230}
+    assert abs(rf.algorithmic_flops("drm19", "ReactorCvode", st) - 1.2e6) < 0.1e6
+    assert rf.algorithmic_flops("LiDryer", "ReactorRK64", {"nst": 10}) == 57960.0
